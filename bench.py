@@ -1,0 +1,400 @@
+#!/usr/bin/env python
+"""bench.py -- forward+backward Gaussians/s of the strand-aligned rasterizer hot path.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl mine|reference] [--mode native|render|render_hair]
+
+Workload (BASELINE.json configs[2], the one `metric` is quoted on): 500 000 synthetic strand-aligned
+Gaussians (SURVEY.md 8d scene "strands(5000)"), 1920x1080, one ring camera per step, forward +
+backward with a fixed random upstream gradient.  A *step* is one pass of the hot path (forward
+rasterize -> backward) over one view.  Inputs are resident in HBM for `value`; `e2e` goes through
+the public Python API (`GaussianRasterizer` + autograd) with the per-view camera and supervision
+tensor copied from pinned host memory and the loss read back every step.
+
+N > 1 (torchrun, one rank per GPU): views shard one per rank per step (weak scaling), the flat
+gradient arena is summed with ONE NCCL all-reduce per step; time is the max over ranks.
+
+`--impl reference` times Oracle-A: the reference's own CUDA extension compiled in place for sm_100a
+(oracle/_ref) -- the reference ships no CPU rasterizer, so that build is the baseline
+(BASELINE.json north_star).  It prints the same JSON line with "impl": "reference".
+
+Prints ONE JSON line on rank 0.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+METRIC = "fwd+bwd Gaussians/s at 500k G, 1080p"
+UNIT = "Gaussians/s"
+
+
+def log(*a):
+    print(*a, file=sys.stderr, flush=True)
+
+
+def parse_args():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=30)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="mine", choices=["mine", "reference"])
+    ap.add_argument("--mode", default="native", choices=["native", "render", "render_hair", "cov3d"])
+    ap.add_argument("--strands", type=int, default=5000)
+    ap.add_argument("--width", type=int, default=1920)
+    ap.add_argument("--height", type=int, default=1080)
+    ap.add_argument("--views", type=int, default=8, help="distinct camera views cycled per rank")
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-roofline", action="store_true")
+    ap.add_argument("--ref-steps", type=int, default=10)
+    return ap.parse_args()
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons DURING the timed region (B200_PROFILING.md recipe)."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+         "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index: int):
+        self.gpu = gpu_index
+        self.proc = None
+        self.path = f"/tmp/gh_clocks_{os.getpid()}.csv"
+
+    def start(self):
+        try:
+            self.f = open(self.path, "w")
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.gpu), f"--query-gpu={self.Q}",
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=self.f, stderr=subprocess.DEVNULL)
+        except Exception:
+            self.proc = None
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        self.f.close()
+        sm, smax, reasons = [], None, set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for line in open(self.path):
+            parts = [p.strip() for p in line.split(",")]
+            if len(parts) < 9:
+                continue
+            try:
+                sm.append(float(parts[1])); smax = float(parts[2])
+            except ValueError:
+                continue
+            for nm, v in zip(names, parts[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(nm)
+        try:
+            os.remove(self.path)
+        except OSError:
+            pass
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": smax,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def measured_peak_gbs():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    try:
+        with open(p) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    except Exception:
+        return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+def algorithmic_bytes(P, R, W, H, T, mode):
+    """Compulsory HBM bytes per stage and for the whole fwd+bwd path (DESIGN.md section 4;
+    path total = SURVEY.md 8(d): 400P + 52R + 96WH + 24T native, 344P when the conic is supplied)."""
+    native = mode in ("native", "cov3d")
+    stage = {
+        "preprocess": (84 if native else 68) * P,
+        "tile_scan": 16 * T,
+        "emit": 24 * P + 8 * R,
+        "tile_sort": 16 * R + 8 * T,
+        "blend_forward": 8 * R + 72 * P + 48 * W * H + 8 * T,
+        "blend_backward": 8 * R + 144 * P + 48 * W * H + 8 * T,
+        "preprocess_backward": 136 * P if native else 0,
+    }
+    path = (400 if native else 344) * P + 52 * R + 96 * W * H + 24 * T
+    return stage, path
+
+
+def main():
+    args = parse_args()
+    import torch
+    import torch.distributed as dist
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.gpus != world and world > 1:
+        log(f"[bench] note: --gpus {args.gpus} but WORLD_SIZE {world}; using WORLD_SIZE")
+    N = world
+
+    if args.impl == "reference" and rank != 0:
+        return 0     # reference arm: rank 0 alone runs and prints
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device (no CPU path exists for this product)")
+    device = torch.device("cuda", local_rank)
+    torch.cuda.set_device(device)
+    use_dist = (N > 1 and args.impl == "mine")
+    if use_dist:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=device)
+
+    from gaussianhaircut_b200 import synth
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import build_ref
+
+    if args.impl == "mine":
+        import gaussianhaircut_b200._C as native
+        import gaussianhaircut_b200 as pkg
+        from gaussianhaircut_b200 import _capi
+        _capi.load()
+    else:
+        if not build_ref.is_built():
+            print(json.dumps({"impl": "reference", "unavailable": "oracle/_ref not built (python oracle/build_ref.py)"}))
+            return 0
+        pkg = build_ref.load()
+        native = pkg._C
+
+    W, H = args.width, args.height
+    gx, gy = (W + 15) // 16, (H + 15) // 16
+    T = gx * gy
+    t0 = time.time()
+    scene = synth.make_strand_scene(args.strands, seed=0)
+    P_total = scene["xyz"].shape[0]
+    views = []
+    for v in range(args.views):
+        cam_k = (rank * args.views + v) % 64 if N > 1 else (v * 8) % 64
+        cam = synth.make_camera(cam_k, W, H)
+        inp = synth.rasterizer_inputs(scene, cam, mode=args.mode, device=device)
+        views.append(inp)
+    dL = synth.upstream_gradient(W, H, 0).to(device)
+    P = views[0]["kwargs"]["means3D"].shape[0]
+    log(f"[bench] rank {rank}: scene P={P_total} (passed to op: {P}), {args.views} views, mode={args.mode}, "
+        f"setup {time.time() - t0:.1f}s")
+
+    def pack_args(inp):
+        kw, s = inp["kwargs"], inp["settings"]
+        e = torch.Tensor([])
+        g = lambda k: e if kw[k] is None else kw[k]  # noqa: E731
+        fw = (s["bg"], kw["means3D"], kw["means2D"], g("colors_precomp"), kw["opacities"], g("scales"), g("rotations"),
+              s["scale_modifier"], g("cov3D_precomp"), g("conic_precomp"), s["viewmatrix"], s["projmatrix"],
+              s["tanfovx"], s["tanfovy"], s["image_height"], s["image_width"], e, s["sh_degree"], s["campos"],
+              s["prefiltered"], False)
+        return fw, kw, s, e, g
+
+    packed = [pack_args(v) for v in views]
+    last = {}
+
+    def step(i, mod=native, arena=(args.impl == "mine")):
+        fw, kw, s, e, g = packed[i % len(packed)]
+        R, color, radii, geom, binning, img = mod.rasterize_gaussians(*fw)
+        bw = (s["bg"], kw["means3D"], radii, g("colors_precomp"), g("scales"), g("rotations"), s["scale_modifier"],
+              g("cov3D_precomp"), g("conic_precomp"), s["viewmatrix"], s["projmatrix"], s["tanfovx"], s["tanfovy"],
+              dL, e, s["sh_degree"], s["campos"], geom, R, binning, img, False)
+        if arena:
+            flat, grads, _ = mod.rasterize_gaussians_backward_arena(*bw)
+            if use_dist:
+                dist.all_reduce(flat, op=dist.ReduceOp.SUM)     # one collective per step over the whole arena
+            last["grads"] = flat
+        else:
+            last["grads"] = mod.rasterize_gaussians_backward(*bw)
+        last["R"] = R
+        return R
+
+    def timed(nsteps, fn):
+        if use_dist:
+            dist.barrier()
+        torch.cuda.synchronize()
+        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        ev0.record()
+        for i in range(nsteps):
+            fn(i)
+        ev1.record()
+        torch.cuda.synchronize()
+        ms = ev0.elapsed_time(ev1)
+        if use_dist:
+            t = torch.tensor([ms], device=device)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms = float(t.item())
+        return ms
+
+    # ---------------------------------------------------------------- device-resident throughput
+    for i in range(args.warmup):
+        step(i)
+    torch.cuda.synchronize()
+    launches0 = None
+    if args.impl == "mine":
+        launches0 = _capi.load().gh_kernel_launch_count()
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    ms_total = timed(args.steps, step)
+    clocks = sampler.stop() if rank == 0 else None
+    gpu_launches = None
+    if args.impl == "mine":
+        gpu_launches = int(_capi.load().gh_kernel_launch_count() - launches0)
+    ms_per_step = ms_total / args.steps
+    value = (args.steps * P * N) / (ms_total * 1e-3)
+    R_mean = float(last["R"])
+    log(f"[bench] {args.impl}: {ms_per_step:.3f} ms/step  -> {value / 1e6:.1f} M Gaussians/s  (R={last['R']})")
+
+    # ---------------------------------------------------------------- end to end through the public API
+    e2e = None
+    if not args.no_e2e:
+        mod = pkg
+        host_views = []
+        for inp in views:
+            s = inp["settings"]
+            host_views.append({
+                "view": s["viewmatrix"].cpu().pin_memory(), "proj": s["projmatrix"].cpu().pin_memory(),
+                "campos": s["campos"].cpu().pin_memory(),
+            })
+        Wt_host = dL.cpu().pin_memory()
+        params = []
+        for inp in views:
+            kw = {k: (v.detach().clone().requires_grad_(True) if isinstance(v, torch.Tensor) else v)
+                  for k, v in inp["kwargs"].items()}
+            params.append(kw)
+        h2d = Wt_host.numel() * 4 + sum(t.numel() * 4 for t in host_views[0].values())
+
+        def e2e_step(i):
+            j = i % len(views)
+            s = views[j]["settings"]
+            hv = host_views[j]
+            view = hv["view"].to(device, non_blocking=True)
+            proj = hv["proj"].to(device, non_blocking=True)
+            campos = hv["campos"].to(device, non_blocking=True)
+            Wt = Wt_host.to(device, non_blocking=True)
+            settings = mod.GaussianRasterizationSettings(
+                image_height=s["image_height"], image_width=s["image_width"], tanfovx=s["tanfovx"],
+                tanfovy=s["tanfovy"], bg=s["bg"], scale_modifier=1.0, viewmatrix=view, projmatrix=proj,
+                sh_degree=s["sh_degree"], campos=campos, prefiltered=s["prefiltered"], debug=False)
+            rast = mod.GaussianRasterizer(raster_settings=settings)
+            kw = params[j]
+            for v in kw.values():
+                if isinstance(v, torch.Tensor):
+                    v.grad = None
+            color, _radii = rast(**kw)
+            loss = (color * Wt).sum()
+            loss.backward()
+            if use_dist:
+                for v in kw.values():
+                    if isinstance(v, torch.Tensor) and v.grad is not None:
+                        dist.all_reduce(v.grad, op=dist.ReduceOp.SUM)
+            last["loss"] = float(loss.item())          # device -> host read of the step's result
+
+        for i in range(min(3, args.warmup)):
+            e2e_step(i)
+        e2e_steps = max(5, args.steps // 2)
+        ms_e2e = timed(e2e_steps, e2e_step)
+        e2e_value = (e2e_steps * P * N) / (ms_e2e * 1e-3)
+        e2e = {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": 4,
+               "ms_per_step": ms_e2e / e2e_steps, "steps": e2e_steps,
+               "api": "GaussianRasterizer(...)(**tensors) + autograd backward; camera + (10,H,W) supervision "
+                      "tensor from pinned host memory and loss.item() every step"}
+        log(f"[bench] e2e: {ms_e2e / e2e_steps:.3f} ms/step -> {e2e_value / 1e6:.1f} M Gaussians/s (loss {last['loss']:.4g})")
+
+    # ---------------------------------------------------------------- per-stage timing -> roofline
+    roofline = None
+    stages = None
+    peak, peak_src = measured_peak_gbs()
+    stage_bytes, path_bytes = algorithmic_bytes(P, last["R"], W, H, T, args.mode)
+    if args.impl == "mine" and rank == 0 and not args.no_roofline:
+        lib = _capi.load()
+        lib.gh_stage_timing_enable(1)
+        nrf = max(5, args.steps // 2)
+        for i in range(nrf):
+            step(i, arena=False)
+        torch.cuda.synchronize()
+        st = _capi.stage_timing_read()
+        lib.gh_stage_timing_enable(0)
+        stages = {}
+        for name, (ms, calls) in st.items():
+            if calls == 0:
+                continue
+            avg = ms / calls
+            gbs = stage_bytes[name] / (avg * 1e-3) / 1e9 if avg > 0 else 0.0
+            stages[name] = {"ms": avg, "alg_bytes": int(stage_bytes[name]), "gbs": gbs, "frac": gbs / peak}
+        dom = max(stages, key=lambda k: stages[k]["ms"])
+        roofline = {"bound": "hbm", "kernel": dom, "achieved": stages[dom]["gbs"], "peak": peak, "unit": "GB/s",
+                    "frac": stages[dom]["frac"], "traffic": None, "peak_source": peak_src,
+                    "ms": stages[dom]["ms"], "alg_bytes": stages[dom]["alg_bytes"],
+                    "timing": f"CUDA events around each stage on the launching stream, {nrf} steps after the timed region"}
+    if use_dist:
+        dist.barrier()
+
+    # ---------------------------------------------------------------- baseline: the reference CUDA build
+    cpu_baseline = None
+    sm_count = torch.cuda.get_device_properties(device).multi_processor_count
+    if args.impl == "mine" and rank == 0 and N == 1 and not args.no_cpu_baseline:
+        if build_ref.is_built():
+            refmod = build_ref.load()._C
+            for i in range(3):
+                step(i, mod=refmod, arena=False)
+            ms_ref = timed(args.ref_steps, lambda i: step(i, mod=refmod, arena=False))
+            ref_value = args.ref_steps * P / (ms_ref * 1e-3)
+            cpu_baseline = {"value": ref_value, "unit": UNIT, "cores": sm_count, "kind": "reference",
+                            "ms_per_step": ms_ref / args.ref_steps,
+                            "sample": f"{args.ref_steps} steps of the same workload; the reference has no CPU rasterizer, "
+                                      f"this is its own CUDA extension (oracle/_ref, sm_100a) on the same B200, {sm_count} SMs"}
+            log(f"[bench] reference CUDA build: {ms_ref / args.ref_steps:.3f} ms/step -> {ref_value / 1e6:.1f} M Gaussians/s")
+        else:
+            cpu_baseline = {"value": None, "unit": UNIT, "cores": sm_count, "kind": "reference",
+                            "sample": "oracle/_ref not built on this box"}
+    if args.impl == "reference":
+        cpu_baseline = {"value": value, "unit": UNIT, "cores": sm_count, "kind": "reference",
+                        "sample": f"{args.steps} steps of the same workload; the reference's own CUDA extension "
+                                  f"(no CPU rasterizer exists), {sm_count} SMs"}
+
+    if rank == 0:
+        path_gbs = path_bytes / (ms_per_step * 1e-3) / 1e9
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": N, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f32", "data": "synthetic",
+            "config": {"workload": f"strands({args.strands}) = {P_total} Gaussians, {W}x{H}, fwd+bwd, mode={args.mode}",
+                       "gaussians_per_view": P, "num_rendered": int(last["R"]), "views_cycled": args.views,
+                       "parallelism": f"views sharded one per GPU (dp{N}), one NCCL all-reduce of the gradient arena per step" if N > 1 else "single GPU",
+                       "l2": "per-step footprint ~0.3 GB (83 MB image + 83 MB upstream grad + 68 MB grads + inputs/workspaces) > 126 MB L2; views cycled"},
+            "clocks": clocks,
+            "e2e": e2e,
+            "gpu_launches": gpu_launches,
+            "roofline": roofline,
+            "path_roofline": {"alg_bytes": int(path_bytes), "achieved": path_gbs, "peak": peak, "unit": "GB/s",
+                              "frac": path_gbs / peak, "formula": "400P+52R+96WH+24T (344P if conic supplied)"},
+            "stages": stages,
+            "cpu_baseline": cpu_baseline,
+        }
+        if args.impl == "reference":
+            line["impl"] = "reference"
+            line["e2e"] = e2e if e2e is not None else {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
+            line["gpu_launches"] = None
+        print(json.dumps(line), flush=True)
+    if use_dist:
+        dist.destroy_process_group()
+    return 0
+
+
+if __name__ == "__main__":
+    sys.exit(main())

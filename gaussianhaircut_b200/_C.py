@@ -1,0 +1,237 @@
+"""Host-side mirror of the reference's native module `diff_gaussian_rasterization._C`.
+
+Same three functions, same positional signatures, same return tuples and error behaviour as the
+reference's torch/pybind binding (ext/diff_gaussian_rasterization_hair/ext.cpp:15-19,
+rasterize_points.cu:35-123, :125-206, :208-227) -- but the work is done by libgh_raster.so through
+its C ABI (include/gh_rasterizer.h).  PyTorch is used for device memory and the current stream only.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Optional, Tuple
+
+import torch
+
+from . import _capi
+
+NUM_CHANNELS = 10  # reference cuda_rasterizer/config.h:15
+
+# floats per Gaussian of each gradient the backward returns (rasterize_points.cu:160-168);
+# they are views into ONE flat zero-filled arena so that a multi-GPU caller can all-reduce
+# everything the op produced with a single collective and no packing copy.
+# (rotations first: the native side stores them as one 16-byte vector per Gaussian)
+_GRAD_LAYOUT = (("rotations", 4), ("conic", 4), ("colors", NUM_CHANNELS), ("cov3D", 6),
+                ("means3D", 3), ("means2D", 3), ("scales", 3), ("opacity", 1))
+GRAD_FLOATS_PER_GAUSSIAN = sum(n for _, n in _GRAD_LAYOUT)
+
+
+def _ptr(t: Optional[torch.Tensor]):
+    """Device pointer or NULL for an absent optional (empty tensor, reference __init__.py:210-222)."""
+    if t is None or t.numel() == 0:
+        return None
+    return C.c_void_p(t.data_ptr())
+
+
+def _prep(t: torch.Tensor, name: str, device: torch.device, align: int = 4) -> torch.Tensor:
+    """contiguous float32 on `device`, like `.contiguous().data<float>()` in the reference binding."""
+    if t.numel() == 0:
+        return t
+    if t.dtype != torch.float32:
+        raise RuntimeError(f"expected scalar type Float but found {t.dtype} for argument '{name}'")
+    if t.device != device:
+        raise RuntimeError(f"argument '{name}' is on {t.device}, expected {device}")
+    t = t.contiguous()
+    if t.data_ptr() % align:
+        t = t.clone()
+    return t
+
+
+def _stream(device: torch.device):
+    return C.c_void_p(torch.cuda.current_stream(device).cuda_stream)
+
+
+def rasterize_gaussians(
+    background: torch.Tensor, means3D: torch.Tensor, means2D_precomp: torch.Tensor,
+    colors: torch.Tensor, opacity: torch.Tensor, scales: torch.Tensor, rotations: torch.Tensor,
+    scale_modifier: float, cov3D_precomp: torch.Tensor, conic_precomp: torch.Tensor,
+    viewmatrix: torch.Tensor, projmatrix: torch.Tensor, tan_fovx: float, tan_fovy: float,
+    image_height: int, image_width: int, sh: torch.Tensor, degree: int, campos: torch.Tensor,
+    prefiltered: bool, debug: bool,
+) -> Tuple[int, torch.Tensor, torch.Tensor, torch.Tensor, torch.Tensor, torch.Tensor]:
+    """RasterizeGaussiansCUDA (rasterize_points.cu:35-123).
+
+    Returns (num_rendered, out_color (C,H,W), radii (P,) int32, geomBuffer, binningBuffer, imgBuffer).
+    """
+    if means3D.ndim != 2 or means3D.size(1) != 3:
+        raise RuntimeError("means3D must have dimensions (num_points, 3)")
+    lib = _capi.load()
+    device = means3D.device
+    if device.type != "cuda":
+        raise RuntimeError("gaussianhaircut_b200 rasterizer: tensors must live on a CUDA device (no CPU path)")
+    P, H, W = int(means3D.size(0)), int(image_height), int(image_width)
+    byte_opts = dict(dtype=torch.uint8, device=device)
+
+    if P == 0:
+        # reference: native call skipped, all-zero image (NOT background), R = 0 (rasterize_points.cu:86-87,122)
+        return (0, torch.zeros((NUM_CHANNELS, H, W), dtype=torch.float32, device=device),
+                torch.zeros((0,), dtype=torch.int32, device=device),
+                torch.empty(0, **byte_opts), torch.empty(0, **byte_opts), torch.empty(0, **byte_opts))
+
+    with torch.cuda.device(device):
+        means3D = _prep(means3D, "means3D", device)
+        colors = _prep(colors, "colors", device, align=8)
+        opacity = _prep(opacity, "opacity", device)
+        scales = _prep(scales, "scales", device)
+        rotations = _prep(rotations, "rotations", device, align=16)
+        cov3D_precomp = _prep(cov3D_precomp, "cov3D_precomp", device)
+        conic_precomp = _prep(conic_precomp, "conic_precomp", device)
+        viewmatrix = _prep(viewmatrix, "viewmatrix", device)
+        projmatrix = _prep(projmatrix, "projmatrix", device)
+        background = _prep(background, "background", device)
+        M = int(sh.size(1)) if sh.numel() != 0 else 0
+
+        geom_bytes, img_bytes = C.c_size_t(), C.c_size_t()
+        _capi.check(lib.gh_forward_workspace_sizes(P, W, H, C.byref(geom_bytes), C.byref(img_bytes)))
+        geomBuffer = torch.empty(geom_bytes.value, **byte_opts)
+        imgBuffer = torch.empty(img_bytes.value, **byte_opts)
+        radii = torch.empty((P,), dtype=torch.int32, device=device)
+        out_color = torch.empty((NUM_CHANNELS, H, W), dtype=torch.float32, device=device)
+        stream = _stream(device)
+
+        n_rendered, max_len = C.c_int(0), C.c_int(0)
+        _capi.check(lib.gh_forward_preprocess(
+            P, int(degree), M, W, H,
+            _ptr(means3D), _ptr(means2D_precomp), _ptr(sh), _ptr(colors), _ptr(opacity),
+            _ptr(scales), float(scale_modifier), _ptr(rotations),
+            _ptr(cov3D_precomp), _ptr(conic_precomp),
+            _ptr(viewmatrix), _ptr(projmatrix), _ptr(campos),
+            float(tan_fovx), float(tan_fovy), int(bool(prefiltered)),
+            _ptr(radii), _ptr(geomBuffer), _ptr(imgBuffer),
+            C.byref(n_rendered), C.byref(max_len), int(bool(debug)), stream))
+        R = int(n_rendered.value)
+
+        bin_bytes = C.c_size_t()
+        _capi.check(lib.gh_binning_workspace_size(R, C.byref(bin_bytes)))
+        binningBuffer = torch.empty(bin_bytes.value, **byte_opts)
+        _capi.check(lib.gh_forward_render(
+            P, W, H, _ptr(background), _ptr(colors), _ptr(radii),
+            _ptr(geomBuffer), _ptr(binningBuffer), _ptr(imgBuffer),
+            R, int(max_len.value), _ptr(out_color), int(bool(debug)), stream))
+    return R, out_color, radii, geomBuffer, binningBuffer, imgBuffer
+
+
+def alloc_grad_arena(P: int, device: torch.device):
+    """One zero-filled flat float32 buffer holding all per-Gaussian gradients + named (P, n) views."""
+    flat = torch.zeros(P * GRAD_FLOATS_PER_GAUSSIAN, dtype=torch.float32, device=device)
+    views, off = {}, 0
+    for name, n in _GRAD_LAYOUT:
+        views[name] = flat[off:off + P * n].view(P, n)
+        off += P * n
+    return flat, views
+
+
+def rasterize_gaussians_backward_arena(
+    background, means3D, radii, colors, scales, rotations, scale_modifier, cov3D_precomp, conic_precomp,
+    viewmatrix, projmatrix, tan_fovx, tan_fovy, dL_dout_color, sh, degree, campos,
+    geomBuffer, R, binningBuffer, imageBuffer, debug,
+):
+    """Same work as `rasterize_gaussians_backward`, but returns (flat_arena, views, dL_dsh): every
+    per-Gaussian gradient is a (P, n) view into ONE flat float32 buffer, which is what a multi-GPU
+    caller all-reduces (one collective per step, no packing copy)."""
+    lib = _capi.load()
+    device = means3D.device
+    P = int(means3D.size(0))
+    H, W = int(dL_dout_color.size(1)), int(dL_dout_color.size(2))
+    M = int(sh.size(1)) if sh.numel() != 0 else 0
+    flat, g = alloc_grad_arena(P, device)
+    dL_dsh = torch.zeros((P, M, 3), dtype=torch.float32, device=device)
+    if P != 0:
+        with torch.cuda.device(device):
+            means3D = _prep(means3D, "means3D", device)
+            colors = _prep(colors, "colors", device, align=8)
+            scales = _prep(scales, "scales", device)
+            rotations = _prep(rotations, "rotations", device, align=16)
+            cov3D_precomp = _prep(cov3D_precomp, "cov3D_precomp", device)
+            conic_precomp = _prep(conic_precomp, "conic_precomp", device)
+            viewmatrix = _prep(viewmatrix, "viewmatrix", device)
+            projmatrix = _prep(projmatrix, "projmatrix", device)
+            background = _prep(background, "background", device)
+            dL_dout_color = _prep(dL_dout_color, "dL_dout_color", device)
+            radii = radii.contiguous()
+            _capi.check(lib.gh_backward(
+                P, int(degree), M, int(R), W, H,
+                _ptr(background), _ptr(means3D), _ptr(sh), _ptr(colors),
+                _ptr(scales), float(scale_modifier), _ptr(rotations),
+                _ptr(cov3D_precomp), _ptr(conic_precomp),
+                _ptr(viewmatrix), _ptr(projmatrix), _ptr(campos),
+                float(tan_fovx), float(tan_fovy), _ptr(radii),
+                _ptr(geomBuffer), _ptr(binningBuffer), _ptr(imageBuffer),
+                _ptr(dL_dout_color),
+                _ptr(g["means2D"]), _ptr(g["conic"]), _ptr(g["opacity"]), _ptr(g["colors"]),
+                _ptr(g["means3D"]), _ptr(g["cov3D"]), _ptr(dL_dsh), _ptr(g["scales"]), _ptr(g["rotations"]),
+                int(bool(debug)), _stream(device)))
+    return flat, g, dL_dsh
+
+
+def rasterize_gaussians_backward(
+    background: torch.Tensor, means3D: torch.Tensor, radii: torch.Tensor, colors: torch.Tensor,
+    scales: torch.Tensor, rotations: torch.Tensor, scale_modifier: float,
+    cov3D_precomp: torch.Tensor, conic_precomp: torch.Tensor,
+    viewmatrix: torch.Tensor, projmatrix: torch.Tensor, tan_fovx: float, tan_fovy: float,
+    dL_dout_color: torch.Tensor, sh: torch.Tensor, degree: int, campos: torch.Tensor,
+    geomBuffer: torch.Tensor, R: int, binningBuffer: torch.Tensor, imageBuffer: torch.Tensor,
+    debug: bool,
+):
+    """RasterizeGaussiansBackwardCUDA (rasterize_points.cu:125-206).
+
+    Returns (dL_dmeans2D (P,3), dL_dcolors (P,C), dL_dopacity (P,1), dL_dmeans3D (P,3), dL_dcov3D (P,6),
+    dL_dconic (P,2,2), dL_dsh (P,M,3), dL_dscales (P,3), dL_drotations (P,4)).
+    """
+    _flat, g, dL_dsh = rasterize_gaussians_backward_arena(
+        background, means3D, radii, colors, scales, rotations, scale_modifier, cov3D_precomp, conic_precomp,
+        viewmatrix, projmatrix, tan_fovx, tan_fovy, dL_dout_color, sh, degree, campos,
+        geomBuffer, R, binningBuffer, imageBuffer, debug)
+    P = int(means3D.size(0))
+    return (g["means2D"], g["colors"], g["opacity"], g["means3D"], g["cov3D"],
+            g["conic"].view(P, 2, 2), dL_dsh, g["scales"], g["rotations"])
+
+
+def mark_visible(means3D: torch.Tensor, viewmatrix: torch.Tensor, projmatrix: torch.Tensor) -> torch.Tensor:
+    """markVisible (rasterize_points.cu:208-227): bool (P,) -- near-plane test only."""
+    lib = _capi.load()
+    device = means3D.device
+    P = int(means3D.size(0))
+    present = torch.zeros((P,), dtype=torch.bool, device=device)
+    if P != 0:
+        with torch.cuda.device(device):
+            means3D = _prep(means3D, "means3D", device)
+            viewmatrix = _prep(viewmatrix, "viewmatrix", device)
+            projmatrix = _prep(projmatrix, "projmatrix", device)
+            _capi.check(lib.gh_mark_visible(P, _ptr(means3D), _ptr(viewmatrix), _ptr(projmatrix),
+                                            _ptr(present), _stream(device)))
+    return present
+
+
+def debug_export(P: int, W: int, H: int, R: int, geomBuffer, binningBuffer, imgBuffer):
+    """Parity-test helper: unpack the opaque workspaces into reference-shaped arrays
+    (keys, point_list, ranges, final_T, n_contrib, depths, means2D, conic_opacity)."""
+    lib = _capi.load()
+    device = geomBuffer.device
+    T = ((W + 15) // 16) * ((H + 15) // 16)
+    out = {
+        "keys": torch.zeros(R, dtype=torch.int64, device=device),
+        "point_list": torch.zeros(R, dtype=torch.int32, device=device),
+        "ranges": torch.zeros((T, 2), dtype=torch.int32, device=device),
+        "final_T": torch.zeros(H * W, dtype=torch.float32, device=device),
+        "n_contrib": torch.zeros(H * W, dtype=torch.int32, device=device),
+        "depths": torch.zeros(P, dtype=torch.float32, device=device),
+        "means2D": torch.zeros((P, 2), dtype=torch.float32, device=device),
+        "conic_opacity": torch.zeros((P, 4), dtype=torch.float32, device=device),
+    }
+    with torch.cuda.device(device):
+        _capi.check(lib.gh_debug_export(
+            P, W, H, R, _ptr(geomBuffer), _ptr(binningBuffer), _ptr(imgBuffer),
+            _ptr(out["keys"]), _ptr(out["point_list"]), _ptr(out["ranges"]),
+            _ptr(out["final_T"]), _ptr(out["n_contrib"]),
+            _ptr(out["depths"]), _ptr(out["means2D"]), _ptr(out["conic_opacity"]), _stream(device)))
+    return out

@@ -1,0 +1,185 @@
+// Stage 2: binning.  Produces, per 16x16 tile, the list of Gaussian instances overlapping it,
+// ordered by the reference's 64-bit key  (tile_id << 32) | float_bits(depth)  with ties broken by
+// ascending Gaussian index -- exactly the order the reference obtains from duplicateWithKeys +
+// a stable cub::DeviceRadixSort::SortPairs over bits [0, 32+bit) + identifyTileRanges
+// (rasterizer_impl.cu:70-138, 293-321).
+//
+// New design (no multi-pass device-wide radix sort): the tile id is an exact bucket, so
+//   1. stage 1 already histogrammed instances per tile;
+//   2. one block scans the histogram -> tile ranges (= identifyTileRanges' output) and R;
+//   3. each Gaussian scatters (depth_bits << 32 | idx) into its tiles' buckets (atomic cursor);
+//   4. each bucket is sorted in shared memory on the composite 64-bit (depth, idx) key, which
+//      reproduces the stable order because a Gaussian appears at most once per tile.
+// HBM traffic is 8 B write + 8 B read + 8 B write per instance instead of ~156 B for 6 radix passes.
+#include "gh_common.cuh"
+#include "gh_kernels.h"
+
+namespace {
+
+// ---------------------------------------------------------------- tile scan (1 block)
+__global__ void __launch_bounds__(1024)
+gh_tile_scan_kernel(int T, const uint32_t* __restrict__ tile_count, uint32_t* __restrict__ tile_cursor,
+                    uint2* __restrict__ ranges, GhCtrl* __restrict__ ctrl)
+{
+    __shared__ uint32_t warp_sums[32];
+    __shared__ uint32_t carry_s;
+    __shared__ uint32_t max_s[32];
+    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    if (tid == 0) carry_s = 0;
+    uint32_t local_max = 0;
+    __syncthreads();
+    for (int base = 0; base < T; base += 1024) {
+        const int i = base + tid;
+        const uint32_t c = (i < T) ? tile_count[i] : 0u;
+        local_max = max(local_max, c);
+        uint32_t v = c;   // inclusive warp scan
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const uint32_t n = __shfl_up_sync(0xffffffffu, v, o);
+            if (lane >= o) v += n;
+        }
+        if (lane == 31) warp_sums[wid] = v;
+        __syncthreads();
+        if (wid == 0) {
+            uint32_t w = warp_sums[lane];
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const uint32_t n = __shfl_up_sync(0xffffffffu, w, o);
+                if (lane >= o) w += n;
+            }
+            warp_sums[lane] = w;   // inclusive over warps
+        }
+        __syncthreads();
+        const uint32_t carry = carry_s;
+        const uint32_t incl = carry + v + (wid > 0 ? warp_sums[wid - 1] : 0u);
+        const uint32_t excl = incl - c;
+        if (i < T) {
+            tile_cursor[i] = excl;
+            // empty tiles keep (0,0) like the reference's memset + identifyTileRanges
+            ranges[i] = (c > 0) ? make_uint2(excl, incl) : make_uint2(0u, 0u);
+        }
+        __syncthreads();
+        if (tid == 1023) carry_s = incl;
+        __syncthreads();
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) local_max = max(local_max, __shfl_xor_sync(0xffffffffu, local_max, o));
+    if (lane == 0) max_s[wid] = local_max;
+    __syncthreads();
+    if (tid == 0) {
+        uint32_t m = 0;
+        for (int w = 0; w < 32; w++) m = max(m, max_s[w]);
+        ctrl->num_rendered = carry_s;
+        ctrl->max_tile_len = m;
+    }
+}
+
+// ---------------------------------------------------------------- emit
+__global__ void __launch_bounds__(256)
+gh_emit_kernel(int P, const int* __restrict__ radii, const GhGeo* __restrict__ geo,
+               const float* __restrict__ depth, uint32_t* __restrict__ tile_cursor,
+               uint64_t* __restrict__ inst, int gx, int gy)
+{
+    const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= P) return;
+    const int r = radii[idx];
+    if (r <= 0) return;
+    const float4 g0 = reinterpret_cast<const float4*>(geo + idx)[0];
+    int minx, miny, maxx, maxy;
+    gh_get_rect(g0.x, g0.y, r, gx, gy, minx, miny, maxx, maxy);
+    const uint64_t rec = ((uint64_t)__float_as_uint(depth[idx]) << 32) | (uint32_t)idx;
+    for (int y = miny; y < maxy; y++)
+        for (int x = minx; x < maxx; x++) {
+            const uint32_t pos = atomicAdd(&tile_cursor[y * gx + x], 1u);
+            inst[pos] = rec;
+        }
+}
+
+// ---------------------------------------------------------------- per-tile sort
+// Normalised bitonic network (every comparator puts the smaller key at the lower index), so
+// elements beyond n behave as +inf without being materialised: a comparator whose upper index
+// is >= n is simply skipped.
+template <typename KeyPtr>
+__device__ __forceinline__ void gh_bitonic_sort(KeyPtr keys, const uint32_t n, const int tid, const int nt)
+{
+    uint32_t n2 = 1;
+    while (n2 < n) n2 <<= 1;
+    const uint32_t half = n2 >> 1;
+    for (uint32_t k = 2; k <= n2; k <<= 1) {
+        {   // first step of the merge: partner = mirror inside the block of size k
+            const uint32_t hk = k >> 1;
+            for (uint32_t t = tid; t < half; t += nt) {
+                const uint32_t blk = t / hk, off = t - blk * hk;
+                const uint32_t i = blk * k + off, j = blk * k + (k - 1 - off);
+                if (j < n) {
+                    const uint64_t a = keys[i], b = keys[j];
+                    if (a > b) { keys[i] = b; keys[j] = a; }
+                }
+            }
+            __syncthreads();
+        }
+        for (uint32_t s = k >> 2; s >= 1; s >>= 1) {
+            for (uint32_t t = tid; t < half; t += nt) {
+                const uint32_t i = ((t / s) * (s << 1)) + (t % s), j = i + s;
+                if (j < n) {
+                    const uint64_t a = keys[i], b = keys[j];
+                    if (a > b) { keys[i] = b; keys[j] = a; }
+                }
+            }
+            __syncthreads();
+        }
+    }
+}
+
+// SMEM_KEYS: capacity of the shared staging buffer; handles tiles with lo < n <= hi.
+// Tiles longer than the buffer are sorted in place in global memory by the same network.
+template <int NT>
+__global__ void __launch_bounds__(NT)
+gh_tile_sort_kernel(const uint2* __restrict__ ranges, uint64_t* inst,
+                    uint32_t lo, uint32_t hi, uint32_t smem_keys)
+{
+    extern __shared__ __align__(16) uint64_t skeys[];
+    const uint2 rg = ranges[blockIdx.x];
+    const uint32_t n = rg.y - rg.x;
+    if (n <= lo || n > hi || n < 2) return;
+    uint64_t* g = inst + rg.x;
+    const int tid = threadIdx.x;
+    if (n <= smem_keys) {
+        for (uint32_t i = tid; i < n; i += NT) skeys[i] = g[i];
+        __syncthreads();
+        gh_bitonic_sort(skeys, n, tid, NT);
+        for (uint32_t i = tid; i < n; i += NT) g[i] = skeys[i];
+    } else {
+        __syncthreads();
+        gh_bitonic_sort(g, n, tid, NT);
+    }
+}
+
+}  // namespace
+
+void gh_launch_tile_scan(int T, GhImgWS img, cudaStream_t stream)
+{
+    gh_tile_scan_kernel<<<1, 1024, 0, stream>>>(T, img.tile_count, img.tile_cursor, img.ranges, img.ctrl);
+}
+
+void gh_launch_emit(int P, const int* radii, GhGeomWS geom, GhImgWS img, GhBinWS bin,
+                    int gx, int gy, cudaStream_t stream)
+{
+    gh_emit_kernel<<<(P + 255) / 256, 256, 0, stream>>>(P, radii, geom.geo, geom.depth,
+                                                        img.tile_cursor, bin.inst, gx, gy);
+}
+
+int gh_launch_tile_sort(int T, unsigned int max_tile_len, GhImgWS img, GhBinWS bin, cudaStream_t stream)
+{
+    if (max_tile_len < 2) return 0;
+    constexpr uint32_t SMALL = 2048;     // 16 KB of keys, 256 threads
+    constexpr uint32_t LARGE = 24576;    // 192 KB of keys, 1024 threads
+    gh_tile_sort_kernel<256><<<T, 256, SMALL * 8, stream>>>(img.ranges, bin.inst, 0u, SMALL, SMALL);
+    if (max_tile_len > SMALL) {
+        cudaFuncSetAttribute(gh_tile_sort_kernel<1024>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                             (int)(LARGE * 8));
+        gh_tile_sort_kernel<1024><<<T, 1024, LARGE * 8, stream>>>(img.ranges, bin.inst, SMALL, 0xffffffffu, LARGE);
+        return 2;
+    }
+    return 1;
+}

@@ -1,0 +1,193 @@
+// Shared device/host definitions for the B200-native strand-aligned Gaussian rasterizer.
+//
+// Replaces (as a fresh design, not a translation) the per-stage plumbing of the reference's
+// ext/diff_gaussian_rasterization_hair/cuda_rasterizer/{config.h, auxiliary.h, rasterizer_impl.h}.
+//
+// Rounding contract: every expression that feeds a *decision* of the reference (tile membership,
+// depth key bits, alpha < 1/255, T < 1e-4) is written with explicit round-to-nearest intrinsics in
+// exactly the operation order nvcc 12.9 emits for the reference sources with its default flags
+// (-fmad=true, IEEE div/sqrt, precise expf): in `a*b + c*d + e` nvcc fuses the LEFT product into
+// the add (fma(a,b,c*d)), never fuses a subtraction, and turns 1.f/x into rcp.rn.  Writing the
+// intrinsics out makes the result independent of this compiler's own contraction choices.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#define GH_NUM_CHANNELS 10   // reference config.h:15
+#define GH_BLOCK_X 16        // reference config.h:16
+#define GH_BLOCK_Y 16        // reference config.h:17
+#define GH_TILE_PIX (GH_BLOCK_X * GH_BLOCK_Y)
+
+// error bits in GhCtrl::err_flags
+#define GH_ERR_PREFILTERED 1u   // a point failed the near cull although prefiltered=true (auxiliary.h:156-160)
+
+#define GH_MUL(a, b) __fmul_rn((a), (b))
+#define GH_ADD(a, b) __fadd_rn((a), (b))
+#define GH_SUB(a, b) __fsub_rn((a), (b))
+#define GH_FMA(a, b, c) __fmaf_rn((a), (b), (c))
+#define GH_DIV(a, b) __fdiv_rn((a), (b))
+#define GH_RCP(a) __frcp_rn((a))
+#define GH_SQRT(a) __fsqrt_rn((a))
+
+// Per-Gaussian 2-D state consumed by both blend kernels: one 32-byte sector per Gaussian.
+//   (x, y)      pixel-space mean                       (reference geomState.means2D)
+//   (ca,cb,cc)  conic, op = opacity                     (reference geomState.conic_opacity)
+//   thr         ln(255*op): the Gaussian can reach alpha >= 1/255 only where power >= -thr
+//   pd          1.0f if the conic is positive definite (cull test valid), else 0.0f
+struct __align__(16) GhGeo {
+    float x, y, ca, cb;
+    float cc, op, thr, pd;
+};
+
+struct GhCtrl {
+    unsigned int num_rendered;   // R = sum of per-tile instance counts
+    unsigned int max_tile_len;   // longest per-tile list
+    unsigned int err_flags;
+    unsigned int pad;
+};
+
+static __host__ __device__ __forceinline__ size_t gh_align_up(size_t v, size_t a) {
+    return (v + a - 1) / a * a;
+}
+
+// ---- opaque workspace layouts (new build is free to choose them: SURVEY.md section 8 a11) ----
+struct GhGeomWS {
+    GhGeo* geo;      // [P]
+    float* depth;    // [P] view-space z (key low word)
+    static __host__ __device__ size_t bytes(size_t P) {
+        return gh_align_up(P * sizeof(GhGeo), 256) + gh_align_up(P * sizeof(float), 256) + 256;
+    }
+    static __host__ __device__ GhGeomWS carve(char* base, size_t P) {
+        GhGeomWS w;
+        size_t off = gh_align_up((size_t)base, 256) - (size_t)base;
+        w.geo = (GhGeo*)(base + off); off += gh_align_up(P * sizeof(GhGeo), 256);
+        w.depth = (float*)(base + off);
+        return w;
+    }
+};
+
+struct GhImgWS {
+    GhCtrl* ctrl;            // [1]
+    uint32_t* tile_count;    // [T]   instances per tile
+    uint32_t* tile_cursor;   // [T]   emit cursors
+    uint2* ranges;           // [T]   (start, end) into the sorted instance list; (0,0) if empty
+    float* final_T;          // [W*H]
+    uint32_t* n_contrib;     // [W*H] 1-based list position of the last blended instance
+    static __host__ __device__ size_t bytes(size_t npix, size_t T) {
+        return 256 + 2 * gh_align_up(T * 4, 256) + gh_align_up(T * 8, 256) +
+               2 * gh_align_up(npix * 4, 256) + 256;
+    }
+    static __host__ __device__ GhImgWS carve(char* base, size_t npix, size_t T) {
+        GhImgWS w;
+        size_t off = gh_align_up((size_t)base, 256) - (size_t)base;
+        w.ctrl = (GhCtrl*)(base + off); off += 256;
+        w.tile_count = (uint32_t*)(base + off); off += gh_align_up(T * 4, 256);
+        w.tile_cursor = (uint32_t*)(base + off); off += gh_align_up(T * 4, 256);
+        w.ranges = (uint2*)(base + off); off += gh_align_up(T * 8, 256);
+        w.final_T = (float*)(base + off); off += gh_align_up(npix * 4, 256);
+        w.n_contrib = (uint32_t*)(base + off);
+        return w;
+    }
+};
+
+struct GhBinWS {
+    uint64_t* inst;   // [R]  (depth_bits << 32 | gaussian_idx), bucketed by tile, sorted within a tile
+    static __host__ __device__ size_t bytes(size_t R) { return gh_align_up(R * 8, 256) + 256; }
+    static __host__ __device__ GhBinWS carve(char* base, size_t R) {
+        GhBinWS w;
+        size_t off = gh_align_up((size_t)base, 256) - (size_t)base;
+        w.inst = (uint64_t*)(base + off);
+        (void)R;
+        return w;
+    }
+};
+
+#ifdef __CUDACC__
+// Tile rectangle of a splat (reference auxiliary.h:46-56, float->int truncation, clamp to grid).
+// PTX of the reference: (p - r) * 0.0625 ; ((p + r) + 16) + (-1)) * 0.0625 ; cvt.rzi ; max.s32 0 ; min.u32 grid
+__device__ __forceinline__ void gh_get_rect(float px, float py, int radius, int gx, int gy,
+                                            int& minx, int& miny, int& maxx, int& maxy) {
+    const float rf = (float)radius;
+    int v;
+    v = __float2int_rz(GH_MUL(GH_SUB(px, rf), 0.0625f)); minx = min(gx, max(0, v));
+    v = __float2int_rz(GH_MUL(GH_SUB(py, rf), 0.0625f)); miny = min(gy, max(0, v));
+    v = __float2int_rz(GH_MUL(GH_ADD(GH_ADD(GH_ADD(px, rf), 16.0f), -1.0f), 0.0625f)); maxx = min(gx, max(0, v));
+    v = __float2int_rz(GH_MUL(GH_ADD(GH_ADD(GH_ADD(py, rf), 16.0f), -1.0f), 0.0625f)); maxy = min(gy, max(0, v));
+}
+
+// World-space 3-D covariance from scale * modifier and a RAW (un-normalised) quaternion
+// (reference forward.cu:118-152; glm column-major products, see oracle/glm_shim).
+// Order of operations transcribed from the reference PTX.
+__device__ __forceinline__ void gh_cov3d(float s0, float s1, float s2, float mod,
+                                         float r, float x, float y, float z, float* cov) {
+    const float sx = GH_MUL(mod, s0), sy = GH_MUL(mod, s1), sz = GH_MUL(mod, s2);
+    const float yy = GH_MUL(y, y), zz = GH_MUL(z, z);
+    const float xy = GH_MUL(x, y), rz = GH_MUL(r, z);
+    const float xz = GH_MUL(x, z), ry = GH_MUL(r, y);
+    const float yz = GH_MUL(y, z), rx = GH_MUL(r, x);
+    const float yy_zz = GH_ADD(yy, zz);
+    const float xx_zz = GH_FMA(x, x, zz);
+    const float xx_yy = GH_FMA(x, x, yy);
+    // R columns (glm::mat3 ctor fills columns)
+    const float R00 = GH_SUB(1.0f, GH_ADD(yy_zz, yy_zz));
+    const float t01 = GH_SUB(xy, rz);  const float R01 = GH_ADD(t01, t01);
+    const float t02 = GH_ADD(ry, xz);  const float R02 = GH_ADD(t02, t02);
+    const float t10 = GH_ADD(xy, rz);  const float R10 = GH_ADD(t10, t10);
+    const float R11 = GH_SUB(1.0f, GH_ADD(xx_zz, xx_zz));
+    const float t12 = GH_SUB(yz, rx);  const float R12 = GH_ADD(t12, t12);
+    const float t20 = GH_SUB(xz, ry);  const float R20 = GH_ADD(t20, t20);
+    const float t21 = GH_ADD(rx, yz);  const float R21 = GH_ADD(t21, t21);
+    const float R22 = GH_SUB(1.0f, GH_ADD(xx_yy, xx_yy));
+    // M = S * R  ->  M[c][r] = s_r * R[c][r]   (the zero terms of S do not change the rounding)
+    const float M00 = GH_MUL(sx, R00), M01 = GH_MUL(sy, R01), M02 = GH_MUL(sz, R02);
+    const float M10 = GH_MUL(sx, R10), M11 = GH_MUL(sy, R11), M12 = GH_MUL(sz, R12);
+    const float M20 = GH_MUL(sx, R20), M21 = GH_MUL(sy, R21), M22 = GH_MUL(sz, R22);
+    // Sigma = transpose(M) * M ; Sigma[j][i] = M[i][0]M[j][0] + M[i][1]M[j][1] + M[i][2]M[j][2]
+    cov[0] = GH_FMA(M02, M02, GH_FMA(M00, M00, GH_MUL(M01, M01)));
+    cov[1] = GH_FMA(M02, M12, GH_FMA(M00, M10, GH_MUL(M01, M11)));
+    cov[2] = GH_FMA(M02, M22, GH_FMA(M00, M20, GH_MUL(M01, M21)));
+    cov[3] = GH_FMA(M12, M12, GH_FMA(M10, M10, GH_MUL(M11, M11)));
+    cov[4] = GH_FMA(M12, M22, GH_FMA(M10, M20, GH_MUL(M11, M21)));
+    cov[5] = GH_FMA(M22, M22, GH_FMA(M20, M20, GH_MUL(M21, M21)));
+}
+
+// power = -0.5f*(ca*dx*dx + cc*dy*dy) - cb*dx*dy  in the reference's rounding order
+// (forward.cu:358-361 / backward.cu:495-499).
+__device__ __forceinline__ float gh_power(float dx, float dy, float ca, float cb, float cc) {
+    const float t1 = GH_MUL(dx, ca);
+    const float t3 = GH_MUL(dy, GH_MUL(dy, cc));
+    const float s = GH_FMA(dx, t1, t3);
+    const float p1 = GH_MUL(s, -0.5f);
+    const float t5 = GH_MUL(dy, GH_MUL(dx, cb));
+    return GH_SUB(p1, t5);
+}
+
+// Conservative test: can a Gaussian reach alpha >= 1/255 on ANY pixel of the integer pixel
+// rectangle [rx0,rx1] x [ry0,ry1]?  Returns true when in doubt.  Skipping a Gaussian that fails
+// this test cannot change any pixel: every pixel of the rectangle would hit the reference's
+// `alpha < 1/255 -> continue` (forward.cu:370) for it.
+__device__ __forceinline__ bool gh_cull_hit(const GhGeo& g, float rx0, float rx1, float ry0, float ry1) {
+    // d = mean - pixel  (same sign convention as the blend)
+    const float dx0 = g.x - rx1, dx1 = g.x - rx0;
+    const float dy0 = g.y - ry1, dy1 = g.y - ry0;
+    const bool inside = (dx0 <= 0.f) & (dx1 >= 0.f) & (dy0 <= 0.f) & (dy1 >= 0.f);
+    const float a = g.ca, b = g.cb, c = g.cc;
+    // minimum of q(d) = a dx^2 + 2 b dx dy + c dy^2 over the box: on one of the four edges
+    const float ia = __frcp_rn(a), ic = __frcp_rn(c);
+    float qmin;
+    {
+        float X = dx0, Y = fminf(fmaxf(-b * X * ic, dy0), dy1);
+        qmin = a * X * X + 2.f * b * X * Y + c * Y * Y;
+        X = dx1; Y = fminf(fmaxf(-b * X * ic, dy0), dy1);
+        qmin = fminf(qmin, a * X * X + 2.f * b * X * Y + c * Y * Y);
+        Y = dy0; X = fminf(fmaxf(-b * Y * ia, dx0), dx1);
+        qmin = fminf(qmin, a * X * X + 2.f * b * X * Y + c * Y * Y);
+        Y = dy1; X = fminf(fmaxf(-b * Y * ia, dx0), dx1);
+        qmin = fminf(qmin, a * X * X + 2.f * b * X * Y + c * Y * Y);
+    }
+    const float mx = fmaxf(fabsf(dx0), fabsf(dx1)), my = fmaxf(fabsf(dy0), fabsf(dy1));
+    const float slack = 1e-3f + 2e-5f * (fabsf(a) * mx * mx + fabsf(c) * my * my + 2.f * fabsf(b) * mx * my);
+    const bool miss = (0.5f * qmin > g.thr + slack);   // false for NaN
+    return inside | (g.pd == 0.f) | !miss;
+}
+#endif  // __CUDACC__

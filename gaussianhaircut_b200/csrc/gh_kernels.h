@@ -1,0 +1,41 @@
+// Internal launcher declarations (one per stage); the public C-ABI lives in include/gh_rasterizer.h.
+#pragma once
+#include "gh_common.cuh"
+
+void gh_launch_preprocess(int P, const float* means3D, const float* scales, float scale_modifier,
+                          const float* rotations, const float* opacities, const float* cov3D_precomp,
+                          const float* conic_precomp, const float* viewmatrix, const float* projmatrix,
+                          int W, int H, float tan_fovx, float tan_fovy, int* radii,
+                          GhGeomWS geom, GhImgWS img, int prefiltered, cudaStream_t stream);
+
+void gh_launch_mark_visible(int P, const float* means3D, const float* viewmatrix, bool* present,
+                            cudaStream_t stream);
+
+// exclusive scan of the tile histogram -> ranges, cursors, R, longest list
+void gh_launch_tile_scan(int T, GhImgWS img, cudaStream_t stream);
+
+// scatter (depth|idx) records into their tile buckets
+void gh_launch_emit(int P, const int* radii, GhGeomWS geom, GhImgWS img, GhBinWS bin,
+                    int gx, int gy, cudaStream_t stream);
+
+// sort every tile bucket by (depth bits, gaussian idx)
+// returns the number of kernels launched
+int gh_launch_tile_sort(int T, unsigned int max_tile_len, GhImgWS img, GhBinWS bin, cudaStream_t stream);
+
+void gh_launch_blend_forward(int W, int H, int gx, int gy, GhGeomWS geom, GhImgWS img, GhBinWS bin,
+                             const float* features, const float* bg, float* out_color,
+                             cudaStream_t stream);
+
+void gh_launch_blend_backward(int W, int H, int gx, int gy, GhGeomWS geom, GhImgWS img, GhBinWS bin,
+                              const float* features, const float* bg, const float* dL_dpix,
+                              float* dL_dmean2D, float* dL_dconic, float* dL_dopacity, float* dL_dcolor,
+                              cudaStream_t stream);
+
+void gh_launch_preprocess_backward(int P, const float* means3D, const int* radii,
+                                   const float* scales, float scale_modifier, const float* rotations,
+                                   const float* cov3D_precomp, const float* conic_precomp,
+                                   const float* viewmatrix, const float* projmatrix,
+                                   int W, int H, float tan_fovx, float tan_fovy,
+                                   const float* dL_dmean2D, const float* dL_dconic,
+                                   float* dL_dmean3D, float* dL_dcov3D, float* dL_dscale, float* dL_drot,
+                                   cudaStream_t stream);

@@ -1,0 +1,173 @@
+/*
+ * gh_rasterizer.h -- C ABI of libgh_raster.so, the B200-native (sm_100a) strand-aligned
+ * differentiable Gaussian rasterizer.
+ *
+ * Drop-in boundary.  These entry points are what the reference's native binding for this path
+ * binds today:
+ *
+ *   reference (ext/diff_gaussian_rasterization_hair)                      replaced by
+ *   --------------------------------------------------------------------  ------------------------------
+ *   CudaRasterizer::Rasterizer::forward   (cuda_rasterizer/rasterizer.h:31-55,   gh_forward_preprocess()
+ *                                          rasterizer_impl.cu:198-340)            + gh_forward_render()
+ *   CudaRasterizer::Rasterizer::backward  (rasterizer.h:57-87,                    gh_backward()
+ *                                          rasterizer_impl.cu:344-441)
+ *   CudaRasterizer::Rasterizer::markVisible (rasterizer.h:24-29,                  gh_mark_visible()
+ *                                          rasterizer_impl.cu:141-153)
+ *   required<GeometryState/ImageState/BinningState>() (rasterizer_impl.h:65-72)   gh_*_workspace_size*()
+ *   the three std::function<char*(size_t)> workspace callbacks                    two-phase protocol below
+ *   (rasterize_points.cu:27-33,75-80)
+ *
+ * Conventions
+ *   - every pointer is a DEVICE pointer to contiguous float32 / int32 data unless stated otherwise;
+ *     NULL means "absent optional" (the reference's empty-tensor convention, __init__.py:210-222);
+ *   - the library allocates nothing and keeps no state between calls; the caller owns all buffers
+ *     (outputs and the three opaque workspaces) and passes the CUDA stream explicitly
+ *     (the reference uses the legacy default stream implicitly);
+ *   - matrices use the reference's row-vector (transposed) convention: viewmatrix[12..14] is the
+ *     translation (auxiliary.h:58-66);
+ *   - return value: 0 on success, a GH_E_* code otherwise; gh_last_error() gives the message for the
+ *     calling thread;
+ *   - `rotations` must be 16-byte aligned, `colors_precomp` 8-byte aligned (128-/64-bit loads).
+ *
+ * Two-phase forward (replaces the resize callbacks; the only host sync is the one the reference has
+ * at rasterizer_impl.cu:285):
+ *   1. gh_forward_workspace_sizes(P, W, H, &geom_bytes, &img_bytes); allocate both.
+ *   2. gh_forward_preprocess(...): runs preprocess + per-tile histogram + scan, then copies the
+ *      instance count R (= the reference's num_rendered) to the host and returns it.
+ *   3. gh_binning_workspace_size(R, &bytes); allocate.
+ *   4. gh_forward_render(...): bucket scatter, per-tile sort, alpha compositing.
+ * The three workspaces must be kept for gh_backward (the reference keeps its three byte tensors on
+ * the autograd ctx, __init__.py:102).
+ */
+#ifndef GH_RASTERIZER_H_INCLUDED
+#define GH_RASTERIZER_H_INCLUDED
+
+#include <stddef.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define GH_NUM_CHANNELS_ABI 10   /* reference config.h:15 */
+
+#define GH_OK 0
+#define GH_E_INVALID_ARG 1      /* bad shape / alignment / missing mandatory input            */
+#define GH_E_NO_COLORS 2        /* "For non-RGB, provide precomputed Gaussian colors!"         */
+                                /* (rasterizer_impl.cu:244-247)                                */
+#define GH_E_CUDA 3             /* a CUDA call or kernel failed                                */
+#define GH_E_PREFILTERED 4      /* a point failed the near cull although prefiltered was set   */
+                                /* (reference: device printf + __trap, auxiliary.h:156-160)    */
+
+typedef void* gh_stream_t;      /* cudaStream_t */
+
+/* ABI version; bumped on any signature change. */
+int gh_abi_version(void);
+
+/* Number of feature channels the library was built for (10). */
+int gh_num_channels(void);
+
+/* Number of CUDA kernels this library has launched since it was loaded (bench `gpu_launches`). */
+unsigned long long gh_kernel_launch_count(void);
+
+/*
+ * Optional per-stage device timing for the roofline report: when enabled every stage is bracketed by
+ * CUDA events on the caller's stream and synchronised (so it perturbs end-to-end time: keep it off in
+ * timed regions).  Stage order: preprocess, tile_scan, emit, tile_sort, blend_forward, blend_backward,
+ * preprocess_backward.  gh_stage_timing_read returns the number of stages.
+ */
+void gh_stage_timing_enable(int on);
+int gh_stage_timing_read(double* ms_sum, unsigned long long* calls, int capacity);
+
+/* Message of the last error on this thread ("" if none). */
+const char* gh_last_error(void);
+
+/* Sizes of the geometry (per-Gaussian) and image (per-pixel / per-tile) workspaces. */
+int gh_forward_workspace_sizes(int P, int width, int height, size_t* geom_bytes, size_t* img_bytes);
+
+/* Size of the binning (per-instance) workspace for R instances. */
+int gh_binning_workspace_size(long long R, size_t* binning_bytes);
+
+/*
+ * Phase 1 of Rasterizer::forward.  Inputs as rasterizer.h:31-55 (D = active SH degree, M = SH
+ * coefficients per Gaussian; `shs` is accepted for signature parity but, as in the reference build
+ * with NUM_CHANNELS = 10, `colors_precomp` is mandatory).  Exactly one of (scales+rotations |
+ * cov3D_precomp) is used when conic_precomp is NULL; when conic_precomp is given the conic is
+ * taken from it.  means2D_precomp is never read (reference forward.cu:201-210).
+ * Writes radii[P].  On return *num_rendered = R and *max_tile_len = longest per-tile list
+ * (host values; the call synchronises `stream`).
+ */
+int gh_forward_preprocess(
+    int P, int D, int M,
+    int width, int height,
+    const float* means3D, const float* means2D_precomp, const float* shs,
+    const float* colors_precomp, const float* opacities,
+    const float* scales, float scale_modifier, const float* rotations,
+    const float* cov3D_precomp, const float* conic_precomp,
+    const float* viewmatrix, const float* projmatrix, const float* cam_pos,
+    float tan_fovx, float tan_fovy, int prefiltered,
+    int* radii,
+    char* geom_buffer, char* img_buffer,
+    int* num_rendered, int* max_tile_len,
+    int debug, gh_stream_t stream);
+
+/*
+ * Phase 2 of Rasterizer::forward: binning + per-tile sort + front-to-back blend.
+ * out_color is (C, H, W) channel-major, fully overwritten (background included).
+ */
+int gh_forward_render(
+    int P, int width, int height,
+    const float* background, const float* colors_precomp,
+    const int* radii,
+    char* geom_buffer, char* binning_buffer, char* img_buffer,
+    int num_rendered, int max_tile_len,
+    float* out_color,
+    int debug, gh_stream_t stream);
+
+/*
+ * Rasterizer::backward (rasterizer.h:57-87).  All nine gradient buffers must be zero-filled by the
+ * caller (the reference's binding does torch::zeros, rasterize_points.cu:160-168); shapes as there:
+ * dL_dmean2D (P,3) [NDC units, z unused], dL_dconic (P,2,2) [.x .y .w used, .y = half the
+ * off-diagonal derivative], dL_dopacity (P,1), dL_dcolor (P,C), dL_dmean3D (P,3), dL_dcov3D (P,6),
+ * dL_dsh (P,M,3) [never written: SH path unreachable with C = 10], dL_dscale (P,3), dL_drot (P,4).
+ */
+int gh_backward(
+    int P, int D, int M, int R,
+    int width, int height,
+    const float* background,
+    const float* means3D, const float* shs, const float* colors_precomp,
+    const float* scales, float scale_modifier, const float* rotations,
+    const float* cov3D_precomp, const float* conic_precomp,
+    const float* viewmatrix, const float* projmatrix, const float* campos,
+    float tan_fovx, float tan_fovy,
+    const int* radii,
+    char* geom_buffer, char* binning_buffer, char* img_buffer,
+    const float* dL_dpix,
+    float* dL_dmean2D, float* dL_dconic, float* dL_dopacity, float* dL_dcolor,
+    float* dL_dmean3D, float* dL_dcov3D, float* dL_dsh, float* dL_dscale, float* dL_drot,
+    int debug, gh_stream_t stream);
+
+/* Rasterizer::markVisible: present[i] = (view-space z of point i > 0.2).  `present` is bool[P]. */
+int gh_mark_visible(int P, const float* means3D, const float* viewmatrix, const float* projmatrix,
+                    unsigned char* present, gh_stream_t stream);
+
+/*
+ * Introspection of the opaque workspaces, for parity tests ("bit-exact tile keys and sort order").
+ * Copies are device->device on `stream`; any output pointer may be NULL.
+ *   keys_sorted[R]   = (tile_id << 32) | float_bits(depth)   in list order (reference point_list_keys)
+ *   point_list[R]    = Gaussian index                        in list order (reference point_list)
+ *   ranges[2*T]      = (start, end) per tile                 (reference imgState.ranges)
+ *   final_T[W*H], n_contrib[W*H]                             (reference accum_alpha, n_contrib)
+ *   depths[P], means2D[2*P], conic_opacity[4*P]              (reference geomState.*)
+ */
+int gh_debug_export(
+    int P, int width, int height, long long R,
+    const char* geom_buffer, const char* binning_buffer, const char* img_buffer,
+    unsigned long long* keys_sorted, unsigned int* point_list, unsigned int* ranges,
+    float* final_T, unsigned int* n_contrib,
+    float* depths, float* means2D, float* conic_opacity,
+    gh_stream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* GH_RASTERIZER_H_INCLUDED */

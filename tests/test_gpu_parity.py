@@ -1,0 +1,237 @@
+"""GPU parity: the sm_100a kernels (through the C ABI) against Oracle-A, the reference extension
+compiled in place (oracle/_ref), on identical seeded inputs.
+
+Gates (BASELINE.json north_star): tile keys + sort order bit-exact; rendered maps and all returned
+gradients within 1e-4 relative.  We additionally require radii / per-Gaussian 2-D state /
+final_T / n_contrib to be bit-identical, because every decision of the reference is reproduced.
+"""
+import numpy as np
+import pytest
+import torch
+
+import _util
+from _util import GRAD_NAMES, rel_err
+
+pytestmark = pytest.mark.gpu
+
+REL_TOL = 1e-4      # north_star tolerance for images and gradients
+
+CASES = [
+    # scene, n, W, H, mode, opacity_mode
+    ("strands", 60, 160, 96, "native", "random"),
+    ("strands", 60, 160, 96, "render", "random"),
+    ("strands", 60, 160, 96, "render_hair", "ones"),
+    ("strands", 200, 250, 187, "native", "random"),        # W, H not multiples of 16
+    ("strands", 200, 250, 187, "cov3d", "random"),
+    ("blobs", 3000, 200, 120, "native", "random"),          # big splats, long lists, raw quaternions
+    ("blobs", 3000, 200, 120, "render", "random"),
+    ("strands", 1000, 512, 512, "native", "random"),        # BASELINE config 2 shape
+    ("strands", 1000, 512, 512, "render_hair", "ones"),
+]
+
+
+def _run_both(inp, device, with_backward=True, seed=0):
+    import gaussianhaircut_b200._C as mine
+    ref = _util.ref_module()._C
+    s = inp["settings"]
+    W, H = s["image_width"], s["image_height"]
+    P = inp["kwargs"]["means3D"].shape[0]
+    args = _util.native_args(inp)
+    r_mine = mine.rasterize_gaussians(*args)
+    r_ref = ref.rasterize_gaussians(*args)
+    torch.cuda.synchronize()
+    out = {"P": P, "W": W, "H": H, "mine": r_mine, "ref": r_ref}
+    out["mine_state"] = {k: v.cpu().numpy() for k, v in
+                         mine.debug_export(P, W, H, r_mine[0], r_mine[3], r_mine[4], r_mine[5]).items()}
+    out["ref_state"] = _util.parse_ref_buffers(P, W, H, r_ref[0], r_ref[3], r_ref[4], r_ref[5])
+    if with_backward:
+        dL = _util.synth.upstream_gradient(W, H, seed).to(device)
+        g_mine = mine.rasterize_gaussians_backward(*_util.backward_args(inp, r_mine[2], dL, r_mine[3], r_mine[0], r_mine[4], r_mine[5]))
+        g_ref = ref.rasterize_gaussians_backward(*_util.backward_args(inp, r_ref[2], dL, r_ref[3], r_ref[0], r_ref[4], r_ref[5]))
+        torch.cuda.synchronize()
+        out["g_mine"], out["g_ref"] = g_mine, g_ref
+    return out
+
+
+def _check_binning(o):
+    ms, rs = o["mine_state"], o["ref_state"]
+    assert o["mine"][0] == o["ref"][0], f"num_rendered {o['mine'][0]} != {o['ref'][0]}"
+    assert torch.equal(o["mine"][2], o["ref"][2]), "radii differ"
+    vis = (o["ref"][2] > 0).cpu().numpy()
+    # per-Gaussian state of visible Gaussians, bit for bit
+    assert np.array_equal(ms["depths"].view(np.uint32)[vis], rs["depths"].view(np.uint32)[vis]), "depth bits differ"
+    assert np.array_equal(ms["means2D"].view(np.uint32)[vis], rs["means2D"].view(np.uint32)[vis]), "means2D bits differ"
+    assert np.array_equal(ms["conic_opacity"].view(np.uint32)[vis], rs["conic_opacity"].view(np.uint32)[vis]), "conic/opacity bits differ"
+    # tile keys and sorted order, bit for bit
+    assert np.array_equal(ms["keys"].view(np.uint64), rs["keys"]), "sorted keys differ"
+    assert np.array_equal(ms["point_list"].view(np.uint32), rs["point_list"]), "sorted point list differs"
+    assert np.array_equal(ms["ranges"].view(np.uint32), rs["ranges"]), "tile ranges differ"
+
+
+def _check_image(o):
+    ms, rs = o["mine_state"], o["ref_state"]
+    img_m, img_r = o["mine"][1], o["ref"][1]
+    assert img_m.shape == img_r.shape
+    assert np.array_equal(ms["n_contrib"].view(np.uint32), rs["n_contrib"]), "n_contrib differs"
+    assert np.array_equal(ms["final_T"].view(np.uint32), rs["final_T"].view(np.uint32)), "final_T bits differ"
+    for ch in range(img_r.shape[0]):
+        e = rel_err(img_m[ch], img_r[ch])
+        assert e <= REL_TOL, f"channel {ch}: rel err {e}"
+    scale = img_r.abs().amax(dim=(1, 2), keepdim=True).clamp_min(1e-12)
+    assert ((img_m - img_r).abs() / scale).max().item() <= REL_TOL
+
+
+def _check_grads(o):
+    for name, gm, gr in zip(GRAD_NAMES, o["g_mine"], o["g_ref"]):
+        assert gm.shape == gr.shape, f"{name}: shape {tuple(gm.shape)} vs {tuple(gr.shape)}"
+        if gr.numel() == 0:
+            continue
+        e = rel_err(gm, gr)
+        assert e <= REL_TOL, f"{name}: norm-relative error {e}"
+        mx = gr.abs().max().item()
+        if mx > 0:
+            worst = (gm - gr).abs().max().item() / mx
+            assert worst <= 1e-3, f"{name}: elementwise error {worst} of max|ref|"
+
+
+@pytest.mark.parametrize("scene,n,W,H,mode,opm", CASES)
+def test_parity_vs_reference(cuda_device, scene, n, W, H, mode, opm):
+    inp = _util.make_inputs(scene, n, W, H, mode, opacity_mode=opm, device=cuda_device)
+    o = _run_both(inp, cuda_device)
+    _check_binning(o)
+    _check_image(o)
+    _check_grads(o)
+
+
+@pytest.mark.parametrize("mode", ["native", "render"])
+def test_parity_full_size(cuda_device, mode):
+    """BASELINE config 3 shape: 500k Gaussians, 1920x1080."""
+    inp = _util.make_inputs("strands", 5000, 1920, 1080, mode, device=cuda_device)
+    o = _run_both(inp, cuda_device)
+    _check_binning(o)
+    _check_image(o)
+    _check_grads(o)
+    # size-independent properties of the binning output
+    ms = o["mine_state"]
+    keys = ms["keys"].view(np.uint64)
+    assert np.all(keys[1:] >= keys[:-1]), "keys not sorted"
+    rg = ms["ranges"].view(np.uint32)
+    lens = (rg[:, 1] - rg[:, 0]).astype(np.int64)
+    assert lens.sum() == o["mine"][0]
+    tiles = (keys >> np.uint64(32)).astype(np.int64)
+    nz = np.nonzero(lens)[0]
+    assert np.array_equal(np.unique(tiles), nz)
+
+
+def test_long_tile_lists(cuda_device):
+    """Tiles with > 2048 instances take the large shared-memory sort; > 24576 the in-place one."""
+    scene = _util.synth.make_blob_scene(60000, seed=3, spread=0.05, max_scale=0.02)
+    cam = _util.synth.make_camera(5, 96, 64)
+    inp = _util.synth.rasterizer_inputs(scene, cam, mode="native", device=cuda_device)
+    o = _run_both(inp, cuda_device)
+    rg = o["mine_state"]["ranges"].view(np.uint32)
+    assert (rg[:, 1] - rg[:, 0]).max() > 24576, "test scene no longer reaches the in-place sort path"
+    _check_binning(o)
+    _check_image(o)
+    _check_grads(o)
+
+
+def test_nothing_visible(cuda_device):
+    """R == 0: every pixel is the background (rasterizer_impl.cu:287-289, forward.cu:393-399)."""
+    import gaussianhaircut_b200._C as mine
+    inp = _util.make_inputs("strands", 20, 64, 48, "native", device=cuda_device)
+    inp["kwargs"]["means3D"] = inp["kwargs"]["means3D"] + torch.tensor([0.0, 0.0, 0.0], device=cuda_device)
+    # look away: mirror the scene behind the camera
+    cam_c = inp["settings"]["campos"]
+    inp["kwargs"]["means3D"] = 2.5 * cam_c[None] + inp["kwargs"]["means3D"]
+    o = _run_both(inp, cuda_device)
+    assert o["mine"][0] == 0 and o["ref"][0] == 0
+    assert torch.equal(o["mine"][1], o["ref"][1])
+    bg = inp["settings"]["bg"]
+    assert torch.equal(o["mine"][1], bg[:, None, None].expand_as(o["mine"][1]))
+    for gm, gr in zip(o["g_mine"], o["g_ref"]):
+        assert torch.equal(gm, gr)
+    assert int((o["mine"][2] != 0).sum()) == 0
+
+
+def test_empty_input(cuda_device):
+    """P == 0 returns an all-zero image, not the background (rasterize_points.cu:86-87,122)."""
+    import gaussianhaircut_b200._C as mine
+    inp = _util.make_inputs("strands", 1, 64, 48, "native", device=cuda_device)
+    kw = inp["kwargs"]
+    for k in ("means3D", "means2D", "opacities", "colors_precomp", "scales", "rotations"):
+        kw[k] = kw[k][:0].contiguous()
+    r = mine.rasterize_gaussians(*_util.native_args(inp))
+    assert r[0] == 0 and r[1].shape == (10, 48, 64) and float(r[1].abs().max()) == 0.0 and r[2].numel() == 0
+    dL = torch.ones(10, 48, 64, device=cuda_device)
+    g = mine.rasterize_gaussians_backward(*_util.backward_args(inp, r[2], dL, r[3], r[0], r[4], r[5]))
+    assert [tuple(t.shape) for t in g] == [(0, 3), (0, 10), (0, 1), (0, 3), (0, 6), (0, 2, 2), (0, 0, 3), (0, 3), (0, 4)]
+
+
+def test_zero_det_conic_dropped(cuda_device):
+    """A supplied conic with zero determinant silently drops the Gaussian (forward.cu:243-245)."""
+    inp = _util.make_inputs("strands", 20, 96, 64, "render", device=cuda_device)
+    inp["kwargs"]["conic_precomp"][::7] = torch.tensor([1.0, 1.0, 1.0], device=cuda_device)
+    o = _run_both(inp, cuda_device)
+    assert int((o["mine"][2][::7] != 0).sum()) == 0
+    _check_binning(o)
+    _check_image(o)
+    _check_grads(o)
+
+
+def test_mark_visible(cuda_device):
+    import gaussianhaircut_b200._C as mine
+    ref = _util.ref_module()._C
+    inp = _util.make_inputs("blobs", 5000, 64, 64, "native", device=cuda_device)
+    pts = inp["kwargs"]["means3D"] * 4.0
+    s = inp["settings"]
+    a = mine.mark_visible(pts, s["viewmatrix"], s["projmatrix"])
+    b = ref.mark_visible(pts, s["viewmatrix"], s["projmatrix"])
+    assert a.dtype == torch.bool and torch.equal(a, b) and 0 < int(a.sum()) < a.numel()
+
+
+def test_public_api_autograd(cuda_device):
+    """Through the drop-in package name, with autograd, against the reference's own Python wrapper."""
+    import diff_gaussian_rasterization as mine
+    ref = _util.ref_module()
+    for mode in ("native", "render", "render_hair"):
+        inp = _util.make_inputs("strands", 100, 200, 150, mode, device=cuda_device)
+        dL = _util.synth.upstream_gradient(200, 150, 1).to(cuda_device)
+        res = []
+        for mod in (mine, ref):
+            kw = {k: (v.clone().requires_grad_(True) if isinstance(v, torch.Tensor) else v) for k, v in inp["kwargs"].items()}
+            rast = mod.GaussianRasterizer(raster_settings=_util.settings_tuple(mod, inp["settings"]))
+            color, radii = rast(**kw)
+            (color * dL).sum().backward()
+            res.append((color.detach(), radii, {k: v.grad for k, v in kw.items() if isinstance(v, torch.Tensor)}))
+        (c0, r0, g0), (c1, r1, g1) = res
+        assert torch.equal(r0, r1)
+        assert rel_err(c0, c1) <= REL_TOL
+        for k in g1:
+            if g1[k] is None:
+                assert g0[k] is None or float(g0[k].abs().max()) == 0.0, k
+                continue
+            assert g0[k] is not None, k
+            assert rel_err(g0[k], g1[k]) <= REL_TOL, f"{mode}/{k}: {rel_err(g0[k], g1[k])}"
+
+
+def test_api_errors(cuda_device):
+    import diff_gaussian_rasterization as mine
+    inp = _util.make_inputs("strands", 5, 64, 48, "native", device=cuda_device)
+    rast = mine.GaussianRasterizer(raster_settings=_util.settings_tuple(mine, inp["settings"]))
+    kw = dict(inp["kwargs"])
+    with pytest.raises(Exception, match="excatly one of either SHs or precomputed colors"):
+        rast(**{**kw, "colors_precomp": None})
+    with pytest.raises(Exception, match="exactly one of either scale/rotation pair"):
+        rast(**{**kw, "cov3D_precomp": torch.zeros(kw["means3D"].shape[0], 6, device=cuda_device)})
+    with pytest.raises(RuntimeError, match="means3D must have dimensions"):
+        rast(**{**kw, "means3D": kw["means3D"].reshape(-1)})
+    # SH input without colours: the reference build (NUM_CHANNELS=10) throws as well
+    with pytest.raises(RuntimeError, match="For non-RGB, provide precomputed Gaussian colors"):
+        rast(**{**kw, "colors_precomp": None, "shs": torch.zeros(kw["means3D"].shape[0], 16, 3, device=cuda_device)})
+    # prefiltered=True with a point behind the near plane: error instead of the reference's device trap
+    s = dict(inp["settings"]); s["prefiltered"] = True
+    rast2 = mine.GaussianRasterizer(raster_settings=_util.settings_tuple(mine, s))
+    bad = kw["means3D"].clone(); bad[0] = 3.0 * s["campos"]
+    with pytest.raises(RuntimeError, match="filtered although prefiltered"):
+        rast2(**{**kw, "means3D": bad})
