@@ -5,10 +5,12 @@
 //
 // Rounding contract: every expression that feeds a *decision* of the reference (tile membership,
 // depth key bits, alpha < 1/255, T < 1e-4) is written with explicit round-to-nearest intrinsics in
-// exactly the operation order nvcc 12.9 emits for the reference sources with its default flags
-// (-fmad=true, IEEE div/sqrt, precise expf): in `a*b + c*d + e` nvcc fuses the LEFT product into
-// the add (fma(a,b,c*d)), never fuses a subtraction, and turns 1.f/x into rcp.rn.  Writing the
-// intrinsics out makes the result independent of this compiler's own contraction choices.
+// exactly the operation order nvcc 12.9 + ptxas emit for the reference sources with its default
+// flags (-fmad=true, IEEE div/sqrt, precise expf), read off the reference build's SASS
+// (cuobjdump -sass oracle/_ref/obj/forward.cu.o): NVVM fuses the LEFT product of `a*b + c*d` into
+// the add, ptxas then also fuses `a*b - c*d` into fma(a,b,-(c*d)) and `m*m - d` into fma(m,m,-d);
+// 1.f/x is an IEEE reciprocal.  Writing the intrinsics out makes the result independent of this
+// compiler's own contraction choices.
 #pragma once
 #include <cuda_runtime.h>
 #include <stdint.h>
@@ -121,22 +123,21 @@ __device__ __forceinline__ void gh_get_rect(float px, float py, int radius, int 
 __device__ __forceinline__ void gh_cov3d(float s0, float s1, float s2, float mod,
                                          float r, float x, float y, float z, float* cov) {
     const float sx = GH_MUL(mod, s0), sy = GH_MUL(mod, s1), sz = GH_MUL(mod, s2);
+    // operation order of the reference SASS (ptxas fuses one product of each +- pair into an FFMA)
     const float yy = GH_MUL(y, y), zz = GH_MUL(z, z);
-    const float xy = GH_MUL(x, y), rz = GH_MUL(r, z);
-    const float xz = GH_MUL(x, z), ry = GH_MUL(r, y);
-    const float yz = GH_MUL(y, z), rx = GH_MUL(r, x);
+    const float xz = GH_MUL(x, z), rx = GH_MUL(r, x), rz = GH_MUL(r, z);
     const float yy_zz = GH_ADD(yy, zz);
     const float xx_zz = GH_FMA(x, x, zz);
     const float xx_yy = GH_FMA(x, x, yy);
     // R columns (glm::mat3 ctor fills columns)
     const float R00 = GH_SUB(1.0f, GH_ADD(yy_zz, yy_zz));
-    const float t01 = GH_SUB(xy, rz);  const float R01 = GH_ADD(t01, t01);
-    const float t02 = GH_ADD(ry, xz);  const float R02 = GH_ADD(t02, t02);
-    const float t10 = GH_ADD(xy, rz);  const float R10 = GH_ADD(t10, t10);
+    const float t01 = GH_FMA(x, y, -rz);   const float R01 = GH_ADD(t01, t01);   // 2(xy - rz)
+    const float t02 = GH_FMA(r, y, xz);    const float R02 = GH_ADD(t02, t02);   // 2(xz + ry)
+    const float t10 = GH_FMA(x, y, rz);    const float R10 = GH_ADD(t10, t10);   // 2(xy + rz)
     const float R11 = GH_SUB(1.0f, GH_ADD(xx_zz, xx_zz));
-    const float t12 = GH_SUB(yz, rx);  const float R12 = GH_ADD(t12, t12);
-    const float t20 = GH_SUB(xz, ry);  const float R20 = GH_ADD(t20, t20);
-    const float t21 = GH_ADD(rx, yz);  const float R21 = GH_ADD(t21, t21);
+    const float t12 = GH_FMA(y, z, -rx);   const float R12 = GH_ADD(t12, t12);   // 2(yz - rx)
+    const float t20 = GH_FMA(-r, y, xz);   const float R20 = GH_ADD(t20, t20);   // 2(xz - ry)
+    const float t21 = GH_FMA(y, z, rx);    const float R21 = GH_ADD(t21, t21);   // 2(yz + rx)
     const float R22 = GH_SUB(1.0f, GH_ADD(xx_yy, xx_yy));
     // M = S * R  ->  M[c][r] = s_r * R[c][r]   (the zero terms of S do not change the rounding)
     const float M00 = GH_MUL(sx, R00), M01 = GH_MUL(sy, R01), M02 = GH_MUL(sz, R02);
@@ -157,9 +158,8 @@ __device__ __forceinline__ float gh_power(float dx, float dy, float ca, float cb
     const float t1 = GH_MUL(dx, ca);
     const float t3 = GH_MUL(dy, GH_MUL(dy, cc));
     const float s = GH_FMA(dx, t1, t3);
-    const float p1 = GH_MUL(s, -0.5f);
     const float t5 = GH_MUL(dy, GH_MUL(dx, cb));
-    return GH_SUB(p1, t5);
+    return GH_FMA(s, -0.5f, -t5);   // SASS: FFMA R, s, -0.5, -t5
 }
 
 // Conservative test: can a Gaussian reach alpha >= 1/255 on ANY pixel of the integer pixel

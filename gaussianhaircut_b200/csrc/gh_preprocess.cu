@@ -108,7 +108,7 @@ gh_preprocess_kernel(int P,
             const float c11 = GH_FMA(T12, A21, GH_FMA(T10, A01, GH_MUL(T11, A11)));
             covx = GH_ADD(c00, 0.3f);
             covz = GH_ADD(c11, 0.3f);
-            det = GH_SUB(GH_MUL(covx, covz), GH_MUL(c01, c01));
+            det = GH_FMA(covx, covz, -GH_MUL(c01, c01));
             if (det == 0.0f) break;
             const float det_inv = GH_RCP(det);
             conx = GH_MUL(covz, det_inv);
@@ -119,7 +119,7 @@ gh_preprocess_kernel(int P,
             conx = conic_precomp[3 * idx + 0];
             cony = conic_precomp[3 * idx + 1];
             conz = conic_precomp[3 * idx + 2];
-            const float det_inv = GH_SUB(GH_MUL(conx, conz), GH_MUL(cony, cony));
+            const float det_inv = GH_FMA(conx, conz, -GH_MUL(cony, cony));
             if (det_inv == 0.0f) break;
             det = GH_RCP(det_inv);
             covx = GH_MUL(conz, det);
@@ -127,7 +127,7 @@ gh_preprocess_kernel(int P,
         }
         // splat extent from the larger eigenvalue (forward.cu:254-257)
         const float mid = GH_MUL(GH_ADD(covx, covz), 0.5f);
-        const float sq = GH_SQRT(fmaxf(GH_SUB(GH_MUL(mid, mid), det), 0.1f));
+        const float sq = GH_SQRT(fmaxf(GH_FMA(mid, mid, -det), 0.1f));
         const float lam = fmaxf(GH_ADD(mid, sq), GH_SUB(mid, sq));
         const float my_radius = ceilf(GH_MUL(GH_SQRT(lam), 3.0f));
         const float pix_x = gh_ndc2pix(projx, W), pix_y = gh_ndc2pix(projy, H);
