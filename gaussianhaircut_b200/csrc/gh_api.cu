@@ -251,6 +251,8 @@ int gh_backward(
         if (dL_drot && ((size_t)dL_drot & 15)) return gh_fail(GH_E_INVALID_ARG, "dL_drot must be 16-byte aligned");
     }
     if (((size_t)colors_precomp & 7)) return gh_fail(GH_E_INVALID_ARG, "colors_precomp must be 8-byte aligned");
+    if (((size_t)dL_dconic & 15)) return gh_fail(GH_E_INVALID_ARG, "dL_dconic must be 16-byte aligned");
+    if (((size_t)dL_dcolor & 7)) return gh_fail(GH_E_INVALID_ARG, "dL_dcolor must be 8-byte aligned");
     int gx, gy; gh_grid(width, height, gx, gy);
     const int T = gx * gy;
     GhGeomWS geom = GhGeomWS::carve(geom_buffer, (size_t)P);
@@ -259,9 +261,11 @@ int gh_backward(
 
     if (R > 0) {
         GhStageTimer t(GH_ST_BLEND_BWD, stream);
-        gh_launch_blend_backward(width, height, gx, gy, geom, img, bin, colors_precomp, background, dL_dpix,
-                                 dL_dmean2D, dL_dconic, dL_dopacity, dL_dcolor, stream);
-        g_launches += 1;
+        cudaError_t e = cudaMemsetAsync(geom.acc16, 0, (size_t)P * 64, stream);
+        if (e != cudaSuccess) return gh_check_cuda(e, "memset(accumulation records)");
+        gh_launch_blend_backward(width, height, gx, gy, geom, img, bin, colors_precomp, background, dL_dpix, stream);
+        gh_launch_unpack_grads(P, geom, dL_dmean2D, dL_dconic, dL_dopacity, dL_dcolor, stream);
+        g_launches += 2;
     }
     GH_STAGE(stream, debug, "blend backward");
     if (conic_precomp == nullptr) {   // reference: geometry backward is a no-op when the conic was supplied

@@ -2,23 +2,31 @@
 // (RGB, label, ones, dir2D(3), orientation confidence, depth) and its back-to-front backward.
 //
 // Per-pixel arithmetic and every skip/stop decision follow the reference kernels renderCUDA
-// (cuda_rasterizer/forward.cu:287-400, backward.cu:403-561) bit for bit; what is new is the work
-// decomposition:
-//   * a tile is blended by 8 warps, each owning an 8x4 pixel block;
-//   * each warp first tests the staged Gaussians against its own 8x4 block with an exact-conservative
-//     "can this splat reach alpha >= 1/255 anywhere in the block" test (one Gaussian per lane) and
-//     then walks only the survivors -- strand Gaussians are long thin ellipses whose 3-sigma square
-//     over-covers most of the tile, so most (pixel, Gaussian) pairs of the reference are skipped here;
-//   * all 10 feature channels are staged in shared memory with the geometry (the reference forward
-//     re-reads them from global memory per contributing pair, forward.cu:381);
-//   * the backward reduces the 16 gradient components of a Gaussian over the 32 pixels of a warp
-//     with a 16-shuffle transposing butterfly and issues ONE red.global.add per component per
-//     (warp, Gaussian) instead of one atomicAdd per component per (pixel, Gaussian)
-//     (backward.cu:527,549-558).
+// (cuda_rasterizer/forward.cu:287-400, backward.cu:403-561) bit for bit.  The work decomposition is
+// new and built around the shape of strand-aligned Gaussians (long thin ellipses: of the 256 pixels
+// of a tile a splat typically reaches alpha >= 1/255 on ~15):
+//
+//   * a tile (16x16 px) is one CTA of 8 warps; its depth-sorted list is staged in chunks of 256
+//     instances into shared memory with cp.async (LDGSTS), double buffered, indices prefetched two
+//     chunks ahead, so the gather latency overlaps the blending of the previous chunk;
+//   * each staged Gaussian is scan-converted ONCE per tile (one lane per Gaussian) against the tile's
+//     32 blocks of 4x2 pixels: the exact-conservative x-span of {alpha >= 1/255} on every pixel row
+//     gives a 32-bit block mask; 32 warp ballots transpose the masks into one 256-bit list per block;
+//   * a block is owned by 8 lanes (a quarter warp).  The four quarter warps of a warp walk their own
+//     lists in lock-step, i.e. every warp instruction works on FOUR different Gaussians -- lane
+//     utilisation roughly doubles against one-Gaussian-per-warp and a skipped Gaussian costs nothing;
+//   * backward: the 16 gradient components of a Gaussian are reduced over the 8 pixels of a block by
+//     a 3-level transposing butterfly (14 shuffles shared by 4 Gaussians), leaving two adjacent
+//     components per lane, which go out as ONE 64-bit vector reduction (REDG.ADD.F32x2) per lane into
+//     a 64-byte per-Gaussian accumulation record -- instead of 16 scalar atomicAdd per (pixel,
+//     Gaussian) pair in the reference (backward.cu:527,549-558);
+//   * dL/dalpha uses the scalar form of the reference's per-channel suffix recursion
+//     (backward.cu:519-523):  sum_ch (c - accum_rec)[ch] dL[ch]  =  c.dL  -  A,   A' = a_last (c_last.dL) + (1-a_last) A.
 #include "gh_common.cuh"
 #include "gh_kernels.h"
 
 #define GH_CHUNK 256
+#define GH_HALF_C (GH_NUM_CHANNELS / 2)
 
 namespace {
 
@@ -42,49 +50,122 @@ __device__ __forceinline__ GhPixEval gh_eval(const float4 g0, const float4 g1, f
     return e;
 }
 
-// stage `cnt` instances (list positions first .. first+cnt-1, ascending or descending) into smem
-__device__ __forceinline__ void gh_stage_chunk(const uint64_t* __restrict__ inst, long long pos, bool valid,
-                                               const GhGeo* __restrict__ geo, const float* __restrict__ features,
-                                               float4* s_g0, float4* s_g1, float2* s_feat, uint32_t* s_id, int slot)
-{
-    if (valid) {
-        const uint32_t id = (uint32_t)inst[pos];
-        const float4* gp = reinterpret_cast<const float4*>(geo + id);
-        const float4 a = __ldg(gp), b = __ldg(gp + 1);
-        const float2* fp = reinterpret_cast<const float2*>(features + (size_t)id * GH_NUM_CHANNELS);
-        float2 f[GH_NUM_CHANNELS / 2];
+__device__ __forceinline__ void gh_cp_async16(void* smem, const void* gmem) {
+    const unsigned s = (unsigned)__cvta_generic_to_shared(smem);
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(s), "l"(gmem));
+}
+__device__ __forceinline__ void gh_cp_async8(void* smem, const void* gmem) {
+    const unsigned s = (unsigned)__cvta_generic_to_shared(smem);
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 8;\n" ::"r"(s), "l"(gmem));
+}
+__device__ __forceinline__ void gh_cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::); }
+__device__ __forceinline__ void gh_cp_async_wait_all() { asm volatile("cp.async.wait_group 0;\n" ::: "memory"); }
+
+struct GhStage {
+    float4 g0[2][GH_CHUNK];
+    float4 g1[2][GH_CHUNK];
+    float2 feat[2][GH_CHUNK * GH_HALF_C];
+    uint32_t id[2][GH_CHUNK];
+    uint32_t bits[32][GH_CHUNK / 32 + 1];   // [block][word]; +1 pad against bank conflicts
+};
+
+// issue the gather of one instance (geometry record + feature row) into slot `slot` of buffer `buf`
+__device__ __forceinline__ void gh_stage_issue(GhStage& st, int buf, int slot, uint32_t id,
+                                               const GhGeo* __restrict__ geo, const float* __restrict__ features) {
+    const float4* gp = reinterpret_cast<const float4*>(geo + id);
+    gh_cp_async16(&st.g0[buf][slot], gp);
+    gh_cp_async16(&st.g1[buf][slot], gp + 1);
+    const float2* fp = reinterpret_cast<const float2*>(features + (size_t)id * GH_NUM_CHANNELS);
 #pragma unroll
-        for (int k = 0; k < GH_NUM_CHANNELS / 2; k++) f[k] = __ldg(fp + k);
-        s_g0[slot] = a; s_g1[slot] = b;
+    for (int k = 0; k < GH_HALF_C; k++) gh_cp_async8(&st.feat[buf][slot * GH_HALF_C + k], fp + k);
+    st.id[buf][slot] = id;
+}
+
+// Which of the tile's 32 blocks (4 wide x 2 high; bit = by*4 + bx) can this Gaussian reach with
+// alpha >= 1/255?  Exact-conservative: on each pixel row the set {q(d) <= 2(thr+slack)} is an
+// x-interval obtained from the quadratic; the interval is widened by 0.01 px and rounded outwards to
+// whole pixels.  Returns all ones when the conic is not positive definite (no bound available).
+// Skipping a Gaussian in a block whose bit is clear cannot change any pixel of that block: each of
+// them would take the reference's `alpha < 1/255 -> continue` (forward.cu:370, backward.cu:503).
+__device__ __forceinline__ uint32_t gh_block_mask(const float4 g0, const float4 g1, float tx0, float ty0) {
+    const float gx = g0.x, gy = g0.y, a = g0.z, b = g0.w, c = g1.x, thr = g1.z, pd = g1.w;
+    if (pd == 0.f) return 0xffffffffu;
+    const float mxd = fmaxf(fabsf(gx - tx0), fabsf(gx - (tx0 + 15.f)));
+    const float myd = fmaxf(fabsf(gy - ty0), fabsf(gy - (ty0 + 15.f)));
+    const float slack = 1e-3f + 2e-5f * (a * mxd * mxd + c * myd * myd + 2.f * fabsf(b) * mxd * myd);
+    const float Q = 2.f * (thr + slack);
+    if (!(Q >= 0.f)) return (Q != Q) ? 0xffffffffu : 0u;
+    const float ia = __frcp_rn(a);
+    const float aQ = a * Q;
+    const float bbac = b * b - a * c;      // <= 0 for a PD conic
+    uint32_t mask = 0;
 #pragma unroll
-        for (int k = 0; k < GH_NUM_CHANNELS / 2; k++) s_feat[slot * (GH_NUM_CHANNELS / 2) + k] = f[k];
-        if (s_id) s_id[slot] = id;
+    for (int by = 0; by < 8; by++) {
+        float xlo = 1e30f, xhi = -1e30f;
+#pragma unroll
+        for (int r = 0; r < 2; r++) {
+            const float dy = gy - (ty0 + (float)(2 * by + r));
+            // a dx^2 + 2 b dy dx + (c dy^2 - Q) <= 0,  dx = gx - px
+            const float disc = fmaf(dy * dy, bbac, aQ);
+            if (disc > 0.f) {
+                const float s = disc * rsqrtf(disc);
+                const float hb = b * dy;
+                xlo = fminf(xlo, gx + (hb - s) * ia);
+                xhi = fmaxf(xhi, gx + (hb + s) * ia);
+            }
+        }
+        // tile-local integer pixel columns inside [xlo - .01, xhi + .01]
+        const float lo = (xlo - 0.01f) - tx0, hi = (xhi + 0.01f) - tx0;
+        const int p0 = max(0, __float2int_ru(lo)), p1 = min(15, __float2int_rd(hi));
+        if (p0 <= p1) {
+            const int b0 = p0 >> 2, b1 = p1 >> 2;
+            mask |= (((2u << (b1 - b0)) - 1u) << b0) << (4 * by);
+        }
     }
+    return mask;
+}
+
+// Build the per-block instance lists of one staged chunk: warp w scan-converts Gaussians
+// [32w, 32w+32) of the chunk (one per lane) and transposes the 32 masks with 32 ballots.
+__device__ __forceinline__ void gh_build_lists(GhStage& st, int buf, int cnt, int warp, int lane,
+                                               float tx0, float ty0) {
+    const int j = warp * 32 + lane;
+    uint32_t m = 0;
+    if (j < cnt) m = gh_block_mask(st.g0[buf][j], st.g1[buf][j], tx0, ty0);
+    uint32_t mine = 0;
+#pragma unroll
+    for (int k = 0; k < 32; k++) {
+        const uint32_t v = __ballot_sync(0xffffffffu, (m >> k) & 1u);
+        if (lane == k) mine = v;
+    }
+    st.bits[lane][warp] = mine;   // block `lane`, word `warp`
 }
 
 // ------------------------------------------------------------------------------------------ forward
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(256, 3)
 gh_blend_forward_kernel(const uint2* __restrict__ ranges, const uint64_t* __restrict__ inst,
                         const GhGeo* __restrict__ geo, const float* __restrict__ features,
                         int W, int H, int gx, const float* __restrict__ bg,
                         float* __restrict__ final_T, uint32_t* __restrict__ n_contrib,
                         float* __restrict__ out)
 {
-    __shared__ float4 s_g0[GH_CHUNK];
-    __shared__ float4 s_g1[GH_CHUNK];
-    __shared__ float2 s_feat[GH_CHUNK * GH_NUM_CHANNELS / 2];
+    __shared__ GhStage st;
 
     const int tile = blockIdx.x;
     const int tx = tile % gx, ty = tile / gx;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int bx0 = tx * GH_BLOCK_X + (warp & 1) * 8, by0 = ty * GH_BLOCK_Y + (warp >> 1) * 4;
-    const int px = bx0 + (lane & 7), py = by0 + (lane >> 3);
+    // block k = 4*warp + (lane >> 3): bx = lane >> 3 (0..3), by = warp (0..7); 8 lanes = 4 x 2 pixels
+    const int blk = 4 * warp + (lane >> 3);
+    const int px = tx * GH_BLOCK_X + 4 * (lane >> 3) + (lane & 3);
+    const int py = ty * GH_BLOCK_Y + 2 * warp + ((lane >> 2) & 1);
     const bool inside = (px < W) && (py < H);
     const float pxf = (float)px, pyf = (float)py;
-    const float rx0 = (float)bx0, rx1 = (float)(bx0 + 7), ry0 = (float)by0, ry1 = (float)(by0 + 3);
+    const float tx0 = (float)(tx * GH_BLOCK_X), ty0 = (float)(ty * GH_BLOCK_Y);
+    const unsigned gshift = lane & 24;
 
     const uint2 rg = ranges[tile];
     const int n = (int)(rg.y - rg.x);
+    const int nchunks = (n + GH_CHUNK - 1) / GH_CHUNK;
 
     float T = 1.0f;
     float C[GH_NUM_CHANNELS];
@@ -92,33 +173,46 @@ gh_blend_forward_kernel(const uint2* __restrict__ ranges, const uint64_t* __rest
     for (int ch = 0; ch < GH_NUM_CHANNELS; ch++) C[ch] = 0.f;
     uint32_t last = 0;
     bool done = !inside;
-    bool warp_done = (__ballot_sync(0xffffffffu, done) == 0xffffffffu);
+    bool gdone = ((__ballot_sync(0xffffffffu, done) >> gshift) & 0xffu) == 0xffu;
+    bool warp_done = (__ballot_sync(0xffffffffu, gdone) == 0xffffffffu);
 
-    for (int base = 0; base < n; base += GH_CHUNK) {
-        // block-wide early exit (reference: __syncthreads_count(done) == BLOCK_SIZE); also the
-        // barrier that protects the staging buffers of the previous chunk
-        if (__syncthreads_and(warp_done)) break;
+    // prologue: chunk 0 in flight, indices of chunk 1 in a register
+    uint32_t next_id = 0;
+    if (nchunks > 0) {
+        if (tid < min(GH_CHUNK, n)) gh_stage_issue(st, 0, tid, (uint32_t)inst[(size_t)rg.x + tid], geo, features);
+        gh_cp_async_commit();
+        if (GH_CHUNK + tid < n) next_id = (uint32_t)inst[(size_t)rg.x + GH_CHUNK + tid];
+    }
+
+    for (int c = 0; c < nchunks; c++) {
+        const int buf = c & 1;
+        const int base = c * GH_CHUNK;
         const int cnt = min(GH_CHUNK, n - base);
-        gh_stage_chunk(inst, (long long)rg.x + base + tid, tid < cnt, geo, features,
-                       s_g0, s_g1, s_feat, nullptr, tid);
+        gh_cp_async_wait_all();
+        // chunk c landed for every thread; everybody is done with chunk c-1 (its buffer and the lists);
+        // block-wide early exit like the reference's __syncthreads_count(done) == BLOCK_SIZE
+        if (__syncthreads_and(warp_done)) break;
+        if (c + 1 < nchunks) {
+            if (base + GH_CHUNK + tid < n) gh_stage_issue(st, buf ^ 1, tid, next_id, geo, features);
+            gh_cp_async_commit();
+            if (base + 2 * GH_CHUNK + tid < n) next_id = (uint32_t)inst[(size_t)rg.x + base + 2 * GH_CHUNK + tid];
+        }
+        gh_build_lists(st, buf, cnt, warp, lane, tx0, ty0);
         __syncthreads();
         if (warp_done) continue;
 
-        for (int sub = 0; sub < cnt; sub += 32) {
-            const int j = sub + lane;
-            bool hit = false;
-            if (j < cnt) {
-                const float4 a = s_g0[j], b = s_g1[j];
-                GhGeo g; g.x = a.x; g.y = a.y; g.ca = a.z; g.cb = a.w; g.cc = b.x; g.op = b.y; g.thr = b.z; g.pd = b.w;
-                hit = gh_cull_hit(g, rx0, rx1, ry0, ry1);
-            }
-            uint32_t mask = __ballot_sync(0xffffffffu, hit);
-            while (mask) {
-                const int bpos = __ffs(mask) - 1;
-                mask &= mask - 1;
-                const int jj = sub + bpos;
+        int wi = -1;
+        uint32_t cur = 0;
+        while (true) {
+            while (cur == 0 && wi < GH_CHUNK / 32 - 1) { wi++; cur = st.bits[blk][wi]; }
+            const bool act = (cur != 0) && !gdone;
+            if (!__any_sync(0xffffffffu, act)) break;
+            if (act) {
+                const int bpos = __ffs(cur) - 1;
+                cur &= cur - 1;
+                const int jj = wi * 32 + bpos;
                 if (!done) {
-                    const float4 g0 = s_g0[jj], g1 = s_g1[jj];
+                    const float4 g0 = st.g0[buf][jj], g1 = st.g1[buf][jj];
                     const GhPixEval e = gh_eval(g0, g1, pxf, pyf);
                     if (e.ok) {
                         const float test_T = GH_MUL(T, GH_SUB(1.0f, e.alpha));
@@ -126,8 +220,8 @@ gh_blend_forward_kernel(const uint2* __restrict__ ranges, const uint64_t* __rest
                             done = true;
                         } else {
 #pragma unroll
-                            for (int k = 0; k < GH_NUM_CHANNELS / 2; k++) {
-                                const float2 f = s_feat[jj * (GH_NUM_CHANNELS / 2) + k];
+                            for (int k = 0; k < GH_HALF_C; k++) {
+                                const float2 f = st.feat[buf][jj * GH_HALF_C + k];
                                 C[2 * k + 0] = GH_FMA(T, GH_MUL(e.alpha, f.x), C[2 * k + 0]);
                                 C[2 * k + 1] = GH_FMA(T, GH_MUL(e.alpha, f.y), C[2 * k + 1]);
                             }
@@ -137,9 +231,11 @@ gh_blend_forward_kernel(const uint2* __restrict__ ranges, const uint64_t* __rest
                     }
                 }
             }
-            if (__ballot_sync(0xffffffffu, done) == 0xffffffffu) { warp_done = true; break; }
+            gdone = ((__ballot_sync(0xffffffffu, done) >> gshift) & 0xffu) == 0xffu;
         }
+        warp_done = (__ballot_sync(0xffffffffu, gdone) == 0xffffffffu);
     }
+    gh_cp_async_wait_all();
 
     if (inside) {
         const size_t pix = (size_t)py * W + px;
@@ -153,60 +249,53 @@ gh_blend_forward_kernel(const uint2* __restrict__ ranges, const uint64_t* __rest
 }
 
 // ------------------------------------------------------------------------------------------ backward
-// 16 values per lane -> lane l ends with the warp-wide sum of value  v(l) = l>>1  (both lanes of a pair hold it)
-__device__ __forceinline__ float gh_warp_reduce16(float (&v)[16], int lane) {
-    float w8[8], w4[4], w2[2], w1;
-    const bool b4 = lane & 16, b3 = lane & 8, b2 = lane & 4, b1 = lane & 2;
+// 16 values per lane, reduced over the 8 lanes of a quarter warp; lane i (0..7) of the quarter ends
+// with the sums of components 2i and 2i+1.
+__device__ __forceinline__ float2 gh_group_reduce16(const float (&v)[16], int lane) {
+    float w8[8], w4[4], w2[2];
+    const bool b2 = lane & 4, b1 = lane & 2, b0 = lane & 1;
 #pragma unroll
     for (int i = 0; i < 8; i++) {
-        const float send = b4 ? v[i] : v[i + 8];
-        const float keep = b4 ? v[i + 8] : v[i];
-        w8[i] = keep + __shfl_xor_sync(0xffffffffu, send, 16);
+        const float send = b2 ? v[i] : v[i + 8];
+        const float keep = b2 ? v[i + 8] : v[i];
+        w8[i] = keep + __shfl_xor_sync(0xffffffffu, send, 4);
     }
 #pragma unroll
     for (int i = 0; i < 4; i++) {
-        const float send = b3 ? w8[i] : w8[i + 4];
-        const float keep = b3 ? w8[i + 4] : w8[i];
-        w4[i] = keep + __shfl_xor_sync(0xffffffffu, send, 8);
+        const float send = b1 ? w8[i] : w8[i + 4];
+        const float keep = b1 ? w8[i + 4] : w8[i];
+        w4[i] = keep + __shfl_xor_sync(0xffffffffu, send, 2);
     }
 #pragma unroll
     for (int i = 0; i < 2; i++) {
-        const float send = b2 ? w4[i] : w4[i + 2];
-        const float keep = b2 ? w4[i + 2] : w4[i];
-        w2[i] = keep + __shfl_xor_sync(0xffffffffu, send, 4);
+        const float send = b0 ? w4[i] : w4[i + 2];
+        const float keep = b0 ? w4[i + 2] : w4[i];
+        w2[i] = keep + __shfl_xor_sync(0xffffffffu, send, 1);
     }
-    {
-        const float send = b1 ? w2[0] : w2[1];
-        const float keep = b1 ? w2[1] : w2[0];
-        w1 = keep + __shfl_xor_sync(0xffffffffu, send, 2);
-    }
-    w1 += __shfl_xor_sync(0xffffffffu, w1, 1);
-    return w1;   // component index = (b4?8:0) + (b3?4:0) + (b2?2:0) + (b1?1:0)
+    return make_float2(w2[0], w2[1]);   // components (8*b2 + 4*b1 + 2*b0) + {0, 1} = 2*(lane&7) + {0, 1}
 }
 
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(256, 3)
 gh_blend_backward_kernel(const uint2* __restrict__ ranges, const uint64_t* __restrict__ inst,
                          const GhGeo* __restrict__ geo, const float* __restrict__ features,
                          int W, int H, int gx, const float* __restrict__ bg,
                          const float* __restrict__ final_T, const uint32_t* __restrict__ n_contrib,
                          const float* __restrict__ dL_dpix,
-                         float* __restrict__ dL_dmean2D, float* __restrict__ dL_dconic,
-                         float* __restrict__ dL_dopacity, float* __restrict__ dL_dcolor)
+                         float* __restrict__ acc16)   // [P][16]: colors 0..9, mean2D x,y, conic x,y,w, opacity
 {
-    __shared__ float4 s_g0[GH_CHUNK];
-    __shared__ float4 s_g1[GH_CHUNK];
-    __shared__ float2 s_feat[GH_CHUNK * GH_NUM_CHANNELS / 2];
-    __shared__ uint32_t s_id[GH_CHUNK];
+    __shared__ GhStage st;
     __shared__ uint32_t s_warp_last[8];
 
     const int tile = blockIdx.x;
     const int tx = tile % gx, ty = tile / gx;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int bx0 = tx * GH_BLOCK_X + (warp & 1) * 8, by0 = ty * GH_BLOCK_Y + (warp >> 1) * 4;
-    const int px = bx0 + (lane & 7), py = by0 + (lane >> 3);
+    const int blk = 4 * warp + (lane >> 3);
+    const int px = tx * GH_BLOCK_X + 4 * (lane >> 3) + (lane & 3);
+    const int py = ty * GH_BLOCK_Y + 2 * warp + ((lane >> 2) & 1);
     const bool inside = (px < W) && (py < H);
     const float pxf = (float)px, pyf = (float)py;
-    const float rx0 = (float)bx0, rx1 = (float)(bx0 + 7), ry0 = (float)by0, ry1 = (float)(by0 + 3);
+    const float tx0 = (float)(tx * GH_BLOCK_X), ty0 = (float)(ty * GH_BLOCK_Y);
+    const unsigned gshift = lane & 24;
     const size_t pix = (size_t)py * W + px;
     const size_t plane = (size_t)H * W;
 
@@ -223,81 +312,95 @@ gh_blend_backward_kernel(const uint2* __restrict__ ranges, const uint64_t* __res
         dL_dpixel[ch] = inside ? dL_dpix[ch * plane + pix] : 0.f;
         bg_dot_dpixel += __ldg(bg + ch) * dL_dpixel[ch];
     }
-    float accum_rec[GH_NUM_CHANNELS], last_color[GH_NUM_CHANNELS];
-#pragma unroll
-    for (int ch = 0; ch < GH_NUM_CHANNELS; ch++) { accum_rec[ch] = 0.f; last_color[ch] = 0.f; }
-    float last_alpha = 0.f;
+    float A = 0.f, last_alpha = 0.f, last_cdot = 0.f;
 
     // pixel-coordinate -> NDC chain rule factors (backward.cu:464-465)
     const float ddelx_dx = 0.5f * W, ddely_dy = 0.5f * H;
 
-    uint32_t warp_last = last;
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) warp_last = max(warp_last, __shfl_xor_sync(0xffffffffu, warp_last, o));
-    if (lane == 0) s_warp_last[warp] = warp_last;
+    // how far does this quarter warp / warp / tile reach into the list?
+    uint32_t glast = last;
+    glast = max(glast, __shfl_xor_sync(0xffffffffu, glast, 4));
+    glast = max(glast, __shfl_xor_sync(0xffffffffu, glast, 2));
+    glast = max(glast, __shfl_xor_sync(0xffffffffu, glast, 1));
+    uint32_t wlast = max(glast, __shfl_xor_sync(0xffffffffu, glast, 8));
+    wlast = max(wlast, __shfl_xor_sync(0xffffffffu, wlast, 16));
+    if (lane == 0) s_warp_last[warp] = wlast;
     __syncthreads();
     uint32_t tile_last = 0;
 #pragma unroll
     for (int w = 0; w < 8; w++) tile_last = max(tile_last, s_warp_last[w]);
-    // nothing beyond tile_last is blended by any pixel of this tile
-    const int n = (int)tile_last;
+    const int n = (int)tile_last;             // nothing beyond is blended by any pixel of this tile
     const int nchunks = (n + GH_CHUNK - 1) / GH_CHUNK;
 
+    // chunks are visited last to first; prologue stages the last chunk
+    uint32_t next_id = 0;
+    if (nchunks > 0) {
+        const int b0 = (nchunks - 1) * GH_CHUNK;
+        if (b0 + tid < n) gh_stage_issue(st, (nchunks - 1) & 1, tid, (uint32_t)inst[(size_t)rg.x + b0 + tid], geo, features);
+        gh_cp_async_commit();
+        if (nchunks > 1) next_id = (uint32_t)inst[(size_t)rg.x + b0 - GH_CHUNK + tid];
+    }
+
     for (int c = nchunks - 1; c >= 0; c--) {
+        const int buf = c & 1;
         const int base = c * GH_CHUNK;
         const int cnt = min(GH_CHUNK, n - base);
+        gh_cp_async_wait_all();
         __syncthreads();
-        gh_stage_chunk(inst, (long long)rg.x + base + tid, tid < cnt, geo, features,
-                       s_g0, s_g1, s_feat, s_id, tid);
+        if (c > 0) {
+            gh_stage_issue(st, buf ^ 1, tid, next_id, geo, features);   // earlier chunks are always full
+            gh_cp_async_commit();
+            if (c > 1) next_id = (uint32_t)inst[(size_t)rg.x + base - 2 * GH_CHUNK + tid];
+        }
+        gh_build_lists(st, buf, cnt, warp, lane, tx0, ty0);
         __syncthreads();
-        if ((uint32_t)base >= warp_last) continue;
+        if ((uint32_t)base >= wlast) continue;
 
-        for (int sub = ((cnt - 1) >> 5) << 5; sub >= 0; sub -= 32) {
-            const int j = sub + lane;
-            bool hit = false;
-            if (j < cnt && (uint32_t)(base + j) < warp_last) {
-                const float4 a = s_g0[j], b = s_g1[j];
-                GhGeo g; g.x = a.x; g.y = a.y; g.ca = a.z; g.cb = a.w; g.cc = b.x; g.op = b.y; g.thr = b.z; g.pd = b.w;
-                hit = gh_cull_hit(g, rx0, rx1, ry0, ry1);
+        int wi = GH_CHUNK / 32;
+        uint32_t cur = 0;
+        while (true) {
+            while (cur == 0 && wi > 0) {
+                wi--;
+                // only list positions < glast can have been blended by a pixel of this quarter warp
+                const int lim = (int)glast - (base + wi * 32);
+                const uint32_t valid = lim >= 32 ? 0xffffffffu : (lim <= 0 ? 0u : ((1u << lim) - 1u));
+                cur = st.bits[blk][wi] & valid;
             }
-            uint32_t mask = __ballot_sync(0xffffffffu, hit);
-            while (mask) {
-                const int bpos = 31 - __clz(mask);   // back to front
-                mask &= ~(1u << bpos);
-                const int jj = sub + bpos;
-                const float4 g0 = s_g0[jj], g1 = s_g1[jj];
-                float v[16];
+            const bool act = (cur != 0);
+            if (!__any_sync(0xffffffffu, act)) break;
+
+            float v[16];
 #pragma unroll
-                for (int k = 0; k < 16; k++) v[k] = 0.f;
-                bool contrib = false;
+            for (int k = 0; k < 16; k++) v[k] = 0.f;
+            bool contrib = false;
+            uint32_t id = 0;
+            if (act) {
+                const int bpos = 31 - __clz(cur);   // back to front
+                cur &= ~(1u << bpos);
+                const int jj = wi * 32 + bpos;
+                id = st.id[buf][jj];
                 // reference: contributor--; if (contributor >= last_contributor) continue;
                 if ((uint32_t)(base + jj) < last) {
+                    const float4 g0 = st.g0[buf][jj], g1 = st.g1[buf][jj];
                     const GhPixEval e = gh_eval(g0, g1, pxf, pyf);
                     if (e.ok) {
                         contrib = true;
                         const float alpha = e.alpha, G = e.G;
                         T = GH_DIV(T, GH_SUB(1.0f, alpha));
                         const float dchannel_dcolor = alpha * T;
-                        float dL_dalpha = 0.f;
+                        float cdot = 0.f;
 #pragma unroll
-                        for (int k = 0; k < GH_NUM_CHANNELS / 2; k++) {
-                            const float2 f = s_feat[jj * (GH_NUM_CHANNELS / 2) + k];
-                            {
-                                const int ch = 2 * k;
-                                accum_rec[ch] = last_alpha * last_color[ch] + (1.f - last_alpha) * accum_rec[ch];
-                                last_color[ch] = f.x;
-                                dL_dalpha += (f.x - accum_rec[ch]) * dL_dpixel[ch];
-                                v[ch] = dchannel_dcolor * dL_dpixel[ch];
-                            }
-                            {
-                                const int ch = 2 * k + 1;
-                                accum_rec[ch] = last_alpha * last_color[ch] + (1.f - last_alpha) * accum_rec[ch];
-                                last_color[ch] = f.y;
-                                dL_dalpha += (f.y - accum_rec[ch]) * dL_dpixel[ch];
-                                v[ch] = dchannel_dcolor * dL_dpixel[ch];
-                            }
+                        for (int k = 0; k < GH_HALF_C; k++) {
+                            const float2 f = st.feat[buf][jj * GH_HALF_C + k];
+                            cdot = fmaf(f.x, dL_dpixel[2 * k], cdot);
+                            cdot = fmaf(f.y, dL_dpixel[2 * k + 1], cdot);
+                            v[2 * k] = dchannel_dcolor * dL_dpixel[2 * k];
+                            v[2 * k + 1] = dchannel_dcolor * dL_dpixel[2 * k + 1];
                         }
-                        dL_dalpha *= T;
+                        // suffix recursion on the dot product (backward.cu:519-523)
+                        A = fmaf(last_alpha, last_cdot, (1.f - last_alpha) * A);
+                        last_cdot = cdot;
+                        float dL_dalpha = (cdot - A) * T;
                         last_alpha = alpha;
                         // alpha also scales how much background shows through (backward.cu:535-538)
                         dL_dalpha += (-T_final / (1.f - alpha)) * bg_dot_dpixel;
@@ -314,22 +417,37 @@ gh_blend_backward_kernel(const uint2* __restrict__ ranges, const uint64_t* __res
                         v[15] = G * dL_dalpha;
                     }
                 }
-                if (__ballot_sync(0xffffffffu, contrib) == 0u) continue;
-                const float sum = gh_warp_reduce16(v, lane);
-                if ((lane & 1) == 0) {
-                    const int comp = lane >> 1;
-                    const uint32_t id = s_id[jj];
-                    float* dst;
-                    if (comp < 10)       dst = dL_dcolor + (size_t)id * GH_NUM_CHANNELS + comp;
-                    else if (comp < 12)  dst = dL_dmean2D + (size_t)id * 3 + (comp - 10);
-                    else if (comp < 14)  dst = dL_dconic + (size_t)id * 4 + (comp - 12);
-                    else if (comp == 14) dst = dL_dconic + (size_t)id * 4 + 3;
-                    else                 dst = dL_dopacity + id;
-                    atomicAdd(dst, sum);
-                }
+            }
+            const uint32_t cm = __ballot_sync(0xffffffffu, contrib);
+            if (cm == 0u) continue;
+            const float2 s = gh_group_reduce16(v, lane);
+            if ((cm >> gshift) & 0xffu) {
+                float2* dst = reinterpret_cast<float2*>(acc16 + (size_t)id * 16) + (lane & 7);
+                atomicAdd(dst, s);    // REDG.E.ADD.F32x2
             }
         }
     }
+    gh_cp_async_wait_all();
+}
+
+// ---------------------------------------------------------------------------- gradient unpack
+// acc16 -> the reference binding's layouts (rasterize_points.cu:160-168): dL_dcolor (P,10),
+// dL_dmean2D (P,3) [z never written by the reference: 0], dL_dconic (P,2,2) [.z unused: 0], dL_dopacity (P,1)
+__global__ void __launch_bounds__(256)
+gh_unpack_grads_kernel(int P, const float* __restrict__ acc16, float* __restrict__ dL_dmean2D,
+                       float* __restrict__ dL_dconic, float* __restrict__ dL_dopacity, float* __restrict__ dL_dcolor)
+{
+    const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= P) return;
+    const float4* a = reinterpret_cast<const float4*>(acc16 + (size_t)idx * 16);
+    const float4 a0 = a[0], a1 = a[1], a2 = a[2], a3 = a[3];
+    float2* dc = reinterpret_cast<float2*>(dL_dcolor + (size_t)idx * GH_NUM_CHANNELS);
+    dc[0] = make_float2(a0.x, a0.y); dc[1] = make_float2(a0.z, a0.w);
+    dc[2] = make_float2(a1.x, a1.y); dc[3] = make_float2(a1.z, a1.w);
+    dc[4] = make_float2(a2.x, a2.y);
+    dL_dmean2D[3 * idx + 0] = a2.z; dL_dmean2D[3 * idx + 1] = a2.w; dL_dmean2D[3 * idx + 2] = 0.f;
+    reinterpret_cast<float4*>(dL_dconic)[idx] = make_float4(a3.x, a3.y, 0.f, a3.z);
+    dL_dopacity[idx] = a3.w;
 }
 
 }  // namespace
@@ -344,10 +462,16 @@ void gh_launch_blend_forward(int W, int H, int gx, int gy, GhGeomWS geom, GhImgW
 
 void gh_launch_blend_backward(int W, int H, int gx, int gy, GhGeomWS geom, GhImgWS img, GhBinWS bin,
                               const float* features, const float* bg, const float* dL_dpix,
-                              float* dL_dmean2D, float* dL_dconic, float* dL_dopacity, float* dL_dcolor,
                               cudaStream_t stream)
 {
     gh_blend_backward_kernel<<<gx * gy, 256, 0, stream>>>(img.ranges, bin.inst, geom.geo, features,
                                                           W, H, gx, bg, img.final_T, img.n_contrib, dL_dpix,
-                                                          dL_dmean2D, dL_dconic, dL_dopacity, dL_dcolor);
+                                                          geom.acc16);
+}
+
+void gh_launch_unpack_grads(int P, GhGeomWS geom, float* dL_dmean2D, float* dL_dconic, float* dL_dopacity,
+                            float* dL_dcolor, cudaStream_t stream)
+{
+    gh_unpack_grads_kernel<<<(P + 255) / 256, 256, 0, stream>>>(P, geom.acc16, dL_dmean2D, dL_dconic,
+                                                                dL_dopacity, dL_dcolor);
 }

@@ -56,14 +56,18 @@ static __host__ __device__ __forceinline__ size_t gh_align_up(size_t v, size_t a
 struct GhGeomWS {
     GhGeo* geo;      // [P]
     float* depth;    // [P] view-space z (key low word)
+    float* acc16;    // [P][16] backward accumulation records (64 B each): dL/d colors 0..9,
+                     //         mean2D.x, mean2D.y, conic.x, conic.y, conic.w, opacity
     static __host__ __device__ size_t bytes(size_t P) {
-        return gh_align_up(P * sizeof(GhGeo), 256) + gh_align_up(P * sizeof(float), 256) + 256;
+        return gh_align_up(P * sizeof(GhGeo), 256) + gh_align_up(P * sizeof(float), 256) +
+               gh_align_up(P * 64, 256) + 256;
     }
     static __host__ __device__ GhGeomWS carve(char* base, size_t P) {
         GhGeomWS w;
         size_t off = gh_align_up((size_t)base, 256) - (size_t)base;
         w.geo = (GhGeo*)(base + off); off += gh_align_up(P * sizeof(GhGeo), 256);
-        w.depth = (float*)(base + off);
+        w.depth = (float*)(base + off); off += gh_align_up(P * sizeof(float), 256);
+        w.acc16 = (float*)(base + off);
         return w;
     }
 };

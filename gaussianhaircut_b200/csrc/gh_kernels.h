@@ -26,10 +26,14 @@ void gh_launch_blend_forward(int W, int H, int gx, int gy, GhGeomWS geom, GhImgW
                              const float* features, const float* bg, float* out_color,
                              cudaStream_t stream);
 
+// accumulates into geom.acc16 (must be zero on entry)
 void gh_launch_blend_backward(int W, int H, int gx, int gy, GhGeomWS geom, GhImgWS img, GhBinWS bin,
                               const float* features, const float* bg, const float* dL_dpix,
-                              float* dL_dmean2D, float* dL_dconic, float* dL_dopacity, float* dL_dcolor,
                               cudaStream_t stream);
+
+// geom.acc16 -> dL_dmean2D (P,3), dL_dconic (P,4), dL_dopacity (P), dL_dcolor (P,10); writes every row
+void gh_launch_unpack_grads(int P, GhGeomWS geom, float* dL_dmean2D, float* dL_dconic, float* dL_dopacity,
+                            float* dL_dcolor, cudaStream_t stream);
 
 void gh_launch_preprocess_backward(int P, const float* means3D, const int* radii,
                                    const float* scales, float scale_modifier, const float* rotations,
