@@ -75,24 +75,45 @@ gh_tile_scan_kernel(int T, const uint32_t* __restrict__ tile_count, uint32_t* __
 }
 
 // ---------------------------------------------------------------- emit
+// Consecutive Gaussians of a strand fall into the same tiles, so the lanes of a warp mostly ask for
+// slots of the same few buckets: lanes that want the same tile in the same loop step are grouped
+// with match.any and their leader reserves all their slots with ONE atomic.
 __global__ void __launch_bounds__(256)
 gh_emit_kernel(int P, const int* __restrict__ radii, const GhGeo* __restrict__ geo,
                const float* __restrict__ depth, uint32_t* __restrict__ tile_cursor,
                uint64_t* __restrict__ inst, int gx, int gy)
 {
     const int idx = blockIdx.x * blockDim.x + threadIdx.x;
-    if (idx >= P) return;
-    const int r = radii[idx];
-    if (r <= 0) return;
-    const float4 g0 = reinterpret_cast<const float4*>(geo + idx)[0];
-    int minx, miny, maxx, maxy;
-    gh_get_rect(g0.x, g0.y, r, gx, gy, minx, miny, maxx, maxy);
-    const uint64_t rec = ((uint64_t)__float_as_uint(depth[idx]) << 32) | (uint32_t)idx;
-    for (int y = miny; y < maxy; y++)
-        for (int x = minx; x < maxx; x++) {
-            const uint32_t pos = atomicAdd(&tile_cursor[y * gx + x], 1u);
-            inst[pos] = rec;
+    const int lane = threadIdx.x & 31;
+    int minx = 0, miny = 0, maxx = 0, maxy = 0;
+    uint64_t rec = 0;
+    if (idx < P) {
+        const int r = radii[idx];
+        if (r > 0) {
+            const float4 g0 = reinterpret_cast<const float4*>(geo + idx)[0];
+            gh_get_rect(g0.x, g0.y, r, gx, gy, minx, miny, maxx, maxy);
+            rec = ((uint64_t)__float_as_uint(depth[idx]) << 32) | (uint32_t)idx;
         }
+    }
+    const int w = maxx - minx;
+    const int count = w * (maxy - miny);
+    int maxcount = count;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) maxcount = max(maxcount, __shfl_xor_sync(0xffffffffu, maxcount, o));
+    int x = minx, y = miny;
+    for (int t = 0; t < maxcount; t++) {
+        const bool have = t < count;
+        const int tile = have ? (y * gx + x) : -1;
+        const uint32_t peers = __match_any_sync(0xffffffffu, tile);
+        if (have) {
+            const int leader = __ffs(peers) - 1;
+            uint32_t base = 0;
+            if (lane == leader) base = atomicAdd(&tile_cursor[tile], (uint32_t)__popc(peers));
+            base = __shfl_sync(peers, base, leader);
+            inst[base + __popc(peers & ((1u << lane) - 1u))] = rec;
+            if (++x == maxx) { x = minx; y++; }
+        }
+    }
 }
 
 // ---------------------------------------------------------------- per-tile sort
@@ -102,15 +123,15 @@ gh_emit_kernel(int P, const int* __restrict__ radii, const GhGeo* __restrict__ g
 template <typename KeyPtr>
 __device__ __forceinline__ void gh_bitonic_sort(KeyPtr keys, const uint32_t n, const int tid, const int nt)
 {
-    uint32_t n2 = 1;
-    while (n2 < n) n2 <<= 1;
-    const uint32_t half = n2 >> 1;
-    for (uint32_t k = 2; k <= n2; k <<= 1) {
+    uint32_t ln2 = 0;                       // n2 = 1 << ln2 >= n
+    while ((1u << ln2) < n) ln2++;
+    const uint32_t half = (1u << ln2) >> 1;
+    for (uint32_t lk = 1; lk <= ln2; lk++) {      // merge blocks of size k = 1 << lk
         {   // first step of the merge: partner = mirror inside the block of size k
-            const uint32_t hk = k >> 1;
+            const uint32_t k = 1u << lk, hk = k >> 1;
             for (uint32_t t = tid; t < half; t += nt) {
-                const uint32_t blk = t / hk, off = t - blk * hk;
-                const uint32_t i = blk * k + off, j = blk * k + (k - 1 - off);
+                const uint32_t blk = t >> (lk - 1), off = t & (hk - 1);
+                const uint32_t i = (blk << lk) + off, j = (blk << lk) + (k - 1 - off);
                 if (j < n) {
                     const uint64_t a = keys[i], b = keys[j];
                     if (a > b) { keys[i] = b; keys[j] = a; }
@@ -118,9 +139,10 @@ __device__ __forceinline__ void gh_bitonic_sort(KeyPtr keys, const uint32_t n, c
             }
             __syncthreads();
         }
-        for (uint32_t s = k >> 2; s >= 1; s >>= 1) {
+        for (int ls = (int)lk - 2; ls >= 0; ls--) {   // strides s = k/4 ... 1
+            const uint32_t s = 1u << ls;
             for (uint32_t t = tid; t < half; t += nt) {
-                const uint32_t i = ((t / s) * (s << 1)) + (t % s), j = i + s;
+                const uint32_t i = ((t >> ls) << (ls + 1)) | (t & (s - 1)), j = i + s;
                 if (j < n) {
                     const uint64_t a = keys[i], b = keys[j];
                     if (a > b) { keys[i] = b; keys[j] = a; }

@@ -141,6 +141,66 @@ __device__ __forceinline__ void gh_build_lists(GhStage& st, int buf, int cnt, in
     st.bits[lane][warp] = mine;   // block `lane`, word `warp`
 }
 
+// Per-PIXEL instance lists of one staged chunk (forward pass).  Warp w scan-converts Gaussians
+// [32w, 32w+32) of the chunk (one per lane): on every pixel row the exact-conservative x-span of
+// {alpha >= 1/255} (same quadratic as gh_block_mask) becomes a 16-bit column mask; two rows form the
+// 32-bit coverage word of the 32 pixels owned by one warp (pixel p = 32*(row/2) + 16*(row%2) + col).
+// The 32 (Gaussian) x 32 (pixel) bit matrix is then transposed inside the warp with 5 shuffle steps,
+// so lane P ends with "which of my warp's 32 Gaussians cover pixel P" and stores it: no atomics, no
+// clearing pass.  pixbits is [word = builder warp][pixel] -> a warp reads consecutive banks.
+__device__ __forceinline__ uint32_t gh_transpose32(uint32_t x, int lane) {
+#pragma unroll
+    for (int s = 16; s >= 1; s >>= 1) {
+        const uint32_t m = (s == 16) ? 0x0000ffffu : (s == 8) ? 0x00ff00ffu : (s == 4) ? 0x0f0f0f0fu
+                         : (s == 2) ? 0x33333333u : 0x55555555u;
+        const uint32_t y = __shfl_xor_sync(0xffffffffu, x, s);
+        x = (lane & s) ? (((y >> s) & m) | (x & ~m)) : ((x & m) | ((y & m) << s));
+    }
+    return x;
+}
+
+__device__ __forceinline__ void gh_build_pixel_lists(const GhStage& st, uint32_t* pixbits, int buf, int cnt,
+                                                     int warp, int lane, float tx0, float ty0) {
+    const int j = warp * 32 + lane;
+    uint32_t rowmask[16];
+#pragma unroll
+    for (int r = 0; r < 16; r++) rowmask[r] = 0u;
+    if (j < cnt) {
+        const float4 g0 = st.g0[buf][j], g1 = st.g1[buf][j];
+        const float gx = g0.x, gy = g0.y, a = g0.z, b = g0.w, c = g1.x, thr = g1.z, pd = g1.w;
+        const float mxd = fmaxf(fabsf(gx - tx0), fabsf(gx - (tx0 + 15.f)));
+        const float myd = fmaxf(fabsf(gy - ty0), fabsf(gy - (ty0 + 15.f)));
+        const float slack = 1e-3f + 2e-5f * (a * mxd * mxd + c * myd * myd + 2.f * fabsf(b) * mxd * myd);
+        const float Q = 2.f * (thr + slack);
+        if (pd == 0.f || Q != Q) {
+#pragma unroll
+            for (int r = 0; r < 16; r++) rowmask[r] = 0xffffu;     // no bound available: every pixel
+        } else if (Q >= 0.f) {
+            const float ia = __frcp_rn(a);
+            const float aQ = a * Q;
+            const float bbac = b * b - a * c;                      // < 0 for a PD conic
+#pragma unroll
+            for (int r = 0; r < 16; r++) {
+                const float dy = gy - (ty0 + (float)r);
+                // a dx^2 + 2 b dy dx + (c dy^2 - Q) <= 0,  dx = gx - px
+                const float disc = fmaf(dy * dy, bbac, aQ);
+                if (disc > 0.f) {
+                    const float sq = disc * rsqrtf(disc);
+                    const float hb = b * dy;
+                    const float lo = (gx + (hb - sq) * ia - 0.01f) - tx0, hi = (gx + (hb + sq) * ia + 0.01f) - tx0;
+                    const int p0 = max(0, __float2int_ru(lo)), p1 = min(15, __float2int_rd(hi));
+                    if (p0 <= p1) rowmask[r] = ((2u << (p1 - p0)) - 1u) << p0;
+                }
+            }
+        }
+    }
+#pragma unroll
+    for (int t = 0; t < 8; t++) {
+        const uint32_t word = rowmask[2 * t] | (rowmask[2 * t + 1] << 16);   // my coverage of warp t's pixels
+        pixbits[warp * 256 + t * 32 + lane] = gh_transpose32(word, lane);    // pixel 32t+lane: bits = Gaussians
+    }
+}
+
 // ------------------------------------------------------------------------------------------ forward
 __global__ void __launch_bounds__(256, 3)
 gh_blend_forward_kernel(const uint2* __restrict__ ranges, const uint64_t* __restrict__ inst,
@@ -149,19 +209,21 @@ gh_blend_forward_kernel(const uint2* __restrict__ ranges, const uint64_t* __rest
                         float* __restrict__ final_T, uint32_t* __restrict__ n_contrib,
                         float* __restrict__ out)
 {
+    // Forward needs no cross-pixel communication, so every lane walks the list of ITS OWN pixel:
+    // a lane only ever touches Gaussians whose alpha >= 1/255 footprint (conservatively) contains
+    // its pixel, whatever the other lanes of the warp are doing.
     __shared__ GhStage st;
+    __shared__ uint32_t pixbits[(GH_CHUNK / 32) * 256];   // [word][pixel]
 
     const int tile = blockIdx.x;
     const int tx = tile % gx, ty = tile / gx;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    // block k = 4*warp + (lane >> 3): bx = lane >> 3 (0..3), by = warp (0..7); 8 lanes = 4 x 2 pixels
-    const int blk = 4 * warp + (lane >> 3);
-    const int px = tx * GH_BLOCK_X + 4 * (lane >> 3) + (lane & 3);
-    const int py = ty * GH_BLOCK_Y + 2 * warp + ((lane >> 2) & 1);
+    // a warp owns two pixel rows: lanes 0..15 row 2*warp, lanes 16..31 row 2*warp+1
+    const int px = tx * GH_BLOCK_X + (lane & 15);
+    const int py = ty * GH_BLOCK_Y + 2 * warp + (lane >> 4);
     const bool inside = (px < W) && (py < H);
     const float pxf = (float)px, pyf = (float)py;
     const float tx0 = (float)(tx * GH_BLOCK_X), ty0 = (float)(ty * GH_BLOCK_Y);
-    const unsigned gshift = lane & 24;
 
     const uint2 rg = ranges[tile];
     const int n = (int)(rg.y - rg.x);
@@ -173,8 +235,7 @@ gh_blend_forward_kernel(const uint2* __restrict__ ranges, const uint64_t* __rest
     for (int ch = 0; ch < GH_NUM_CHANNELS; ch++) C[ch] = 0.f;
     uint32_t last = 0;
     bool done = !inside;
-    bool gdone = ((__ballot_sync(0xffffffffu, done) >> gshift) & 0xffu) == 0xffu;
-    bool warp_done = (__ballot_sync(0xffffffffu, gdone) == 0xffffffffu);
+    bool warp_done = (__ballot_sync(0xffffffffu, done) == 0xffffffffu);
 
     // prologue: chunk 0 in flight, indices of chunk 1 in a register
     uint32_t next_id = 0;
@@ -189,51 +250,43 @@ gh_blend_forward_kernel(const uint2* __restrict__ ranges, const uint64_t* __rest
         const int base = c * GH_CHUNK;
         const int cnt = min(GH_CHUNK, n - base);
         gh_cp_async_wait_all();
-        // chunk c landed for every thread; everybody is done with chunk c-1 (its buffer and the lists);
-        // block-wide early exit like the reference's __syncthreads_count(done) == BLOCK_SIZE
+        // chunk c landed for every thread; block-wide early exit like the reference's
+        // __syncthreads_count(done) == BLOCK_SIZE
         if (__syncthreads_and(warp_done)) break;
         if (c + 1 < nchunks) {
             if (base + GH_CHUNK + tid < n) gh_stage_issue(st, buf ^ 1, tid, next_id, geo, features);
             gh_cp_async_commit();
             if (base + 2 * GH_CHUNK + tid < n) next_id = (uint32_t)inst[(size_t)rg.x + base + 2 * GH_CHUNK + tid];
         }
-        gh_build_lists(st, buf, cnt, warp, lane, tx0, ty0);
+        gh_build_pixel_lists(st, pixbits, buf, cnt, warp, lane, tx0, ty0);
         __syncthreads();
-        if (warp_done) continue;
 
-        int wi = -1;
-        uint32_t cur = 0;
-        while (true) {
-            while (cur == 0 && wi < GH_CHUNK / 32 - 1) { wi++; cur = st.bits[blk][wi]; }
-            const bool act = (cur != 0) && !gdone;
-            if (!__any_sync(0xffffffffu, act)) break;
-            if (act) {
+        if (!done) {
+            int wi = 0;
+            uint32_t cur = pixbits[tid];
+            while (true) {
+                while (cur == 0u && wi < GH_CHUNK / 32 - 1) { wi++; cur = pixbits[wi * 256 + tid]; }
+                if (cur == 0u) break;
                 const int bpos = __ffs(cur) - 1;
                 cur &= cur - 1;
                 const int jj = wi * 32 + bpos;
-                if (!done) {
-                    const float4 g0 = st.g0[buf][jj], g1 = st.g1[buf][jj];
-                    const GhPixEval e = gh_eval(g0, g1, pxf, pyf);
-                    if (e.ok) {
-                        const float test_T = GH_MUL(T, GH_SUB(1.0f, e.alpha));
-                        if (test_T < 0.0001f) {
-                            done = true;
-                        } else {
+                const float4 g0 = st.g0[buf][jj], g1 = st.g1[buf][jj];
+                const GhPixEval e = gh_eval(g0, g1, pxf, pyf);
+                if (e.ok) {
+                    const float test_T = GH_MUL(T, GH_SUB(1.0f, e.alpha));
+                    if (test_T < 0.0001f) { done = true; break; }
 #pragma unroll
-                            for (int k = 0; k < GH_HALF_C; k++) {
-                                const float2 f = st.feat[buf][jj * GH_HALF_C + k];
-                                C[2 * k + 0] = GH_FMA(T, GH_MUL(e.alpha, f.x), C[2 * k + 0]);
-                                C[2 * k + 1] = GH_FMA(T, GH_MUL(e.alpha, f.y), C[2 * k + 1]);
-                            }
-                            T = test_T;
-                            last = (uint32_t)(base + jj + 1);
-                        }
+                    for (int k = 0; k < GH_HALF_C; k++) {
+                        const float2 f = st.feat[buf][jj * GH_HALF_C + k];
+                        C[2 * k + 0] = GH_FMA(T, GH_MUL(e.alpha, f.x), C[2 * k + 0]);
+                        C[2 * k + 1] = GH_FMA(T, GH_MUL(e.alpha, f.y), C[2 * k + 1]);
                     }
+                    T = test_T;
+                    last = (uint32_t)(base + jj + 1);
                 }
             }
-            gdone = ((__ballot_sync(0xffffffffu, done) >> gshift) & 0xffu) == 0xffu;
         }
-        warp_done = (__ballot_sync(0xffffffffu, gdone) == 0xffffffffu);
+        warp_done = (__ballot_sync(0xffffffffu, done) == 0xffffffffu);
     }
     gh_cp_async_wait_all();
 

@@ -36,18 +36,21 @@ gh_preprocess_kernel(int P,
                      int gx, int gy, int prefiltered)
 {
     const int idx = blockIdx.x * blockDim.x + threadIdx.x;
-    if (idx >= P) return;
+    const bool valid = idx < P;
 
     // radius 0 <=> "not rendered" (forward.cu:190-191)
     int out_radius = 0;
+    int rect_minx = 0, rect_miny = 0, rect_maxx = 0, rect_maxy = 0;
     GhGeo g; g.x = 0.f; g.y = 0.f; g.ca = 0.f; g.cb = 0.f; g.cc = 0.f; g.op = 0.f; g.thr = -1e30f; g.pd = 0.f;
     float zview = 0.f;
 
-    const float px = means3D[3 * idx + 0], py = means3D[3 * idx + 1], pz = means3D[3 * idx + 2];
+    float px = 0.f, py = 0.f, pz = 0.f;
+    if (valid) { px = means3D[3 * idx + 0]; py = means3D[3 * idx + 1]; pz = means3D[3 * idx + 2]; }
     const float* vm = viewmatrix;
     const float* pm = projmatrix;
 
     do {
+        if (!valid) break;
         // near cull only (auxiliary.h:154)
         zview = GH_ADD(__ldg(vm + 14), GH_FMA(pz, __ldg(vm + 10), GH_FMA(px, __ldg(vm + 2), GH_MUL(py, __ldg(vm + 6)))));
         if (zview <= 0.2f) {
@@ -145,17 +148,38 @@ gh_preprocess_kernel(int P,
         g.pd = pd ? 1.0f : 0.0f;
         if (!(op == op)) g.thr = 1e30f;        // NaN opacity blends with alpha 0.99 in the reference (min.f32)
 
-        // per-tile histogram (replaces the reference's per-Gaussian tiles_touched + prefix sum)
-        for (int y = miny; y < maxy; y++)
-            for (int x = minx; x < maxx; x++)
-                atomicAdd(&tile_count[y * gx + x], 1u);
+        rect_minx = minx; rect_miny = miny; rect_maxx = maxx; rect_maxy = maxy;
     } while (false);
 
-    radii[idx] = out_radius;
-    depth[idx] = zview;
-    float4* gp = reinterpret_cast<float4*>(geo + idx);
-    gp[0] = make_float4(g.x, g.y, g.ca, g.cb);
-    gp[1] = make_float4(g.cc, g.op, g.thr, g.pd);
+    if (valid) {
+        radii[idx] = out_radius;
+        depth[idx] = zview;
+        float4* gp = reinterpret_cast<float4*>(geo + idx);
+        gp[0] = make_float4(g.x, g.y, g.ca, g.cb);
+        gp[1] = make_float4(g.cc, g.op, g.thr, g.pd);
+    }
+
+    // per-tile histogram (replaces the reference's per-Gaussian tiles_touched + prefix sum).
+    // Neighbouring Gaussians of a strand hit the same tiles: lanes asking for the same tile in the same
+    // step are grouped with match.any and counted with one atomic.
+    {
+        const int lane = threadIdx.x & 31;
+        const int w = rect_maxx - rect_minx;
+        const int count = w * (rect_maxy - rect_miny);
+        int maxcount = count;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) maxcount = max(maxcount, __shfl_xor_sync(0xffffffffu, maxcount, o));
+        int x = rect_minx, y = rect_miny;
+        for (int t = 0; t < maxcount; t++) {
+            const bool have = t < count;
+            const int tile = have ? (y * gx + x) : -1;
+            const uint32_t peers = __match_any_sync(0xffffffffu, tile);
+            if (have) {
+                if (lane == __ffs(peers) - 1) atomicAdd(&tile_count[tile], (uint32_t)__popc(peers));
+                if (++x == rect_maxx) { x = rect_minx; y++; }
+            }
+        }
+    }
 }
 
 // markVisible (rasterizer_impl.cu:54-66): near-plane test only.
