@@ -302,33 +302,90 @@ gh_blend_forward_kernel(const uint2* __restrict__ ranges, const uint64_t* __rest
 }
 
 // ------------------------------------------------------------------------------------------ backward
-// 16 values per lane, reduced over the 8 lanes of a quarter warp; lane i (0..7) of the quarter ends
-// with the sums of components 2i and 2i+1.
-__device__ __forceinline__ float2 gh_group_reduce16(const float (&v)[16], int lane) {
-    float w8[8], w4[4], w2[2];
-    const bool b2 = lane & 4, b1 = lane & 2, b0 = lane & 1;
+// CTA = tile = 4 warps.  A lane owns a vertical pixel pair (x, y0), (x, y0+1); 4 lanes own a 4x2 block;
+// the 8 blocks of a warp walk their own lists in lock-step, i.e. every warp instruction works on EIGHT
+// different Gaussians.  The two pixels of a lane are summed in registers; the 16 gradient components
+// are then reduced over the 4 lanes by a 2-level transposing butterfly (12 shuffles shared by 8
+// Gaussians), leaving four adjacent components per lane = one REDG.E.ADD.F32x4 per lane.
+#define GH_BWD_THREADS 128
+
+__device__ __forceinline__ float4 gh_group4_reduce16(const float (&v)[16], int lane) {
+    float w8[8], w4[4];
+    const bool b1 = lane & 2, b0 = lane & 1;
 #pragma unroll
     for (int i = 0; i < 8; i++) {
-        const float send = b2 ? v[i] : v[i + 8];
-        const float keep = b2 ? v[i + 8] : v[i];
-        w8[i] = keep + __shfl_xor_sync(0xffffffffu, send, 4);
+        const float send = b1 ? v[i] : v[i + 8];
+        const float keep = b1 ? v[i + 8] : v[i];
+        w8[i] = keep + __shfl_xor_sync(0xffffffffu, send, 2);
     }
 #pragma unroll
     for (int i = 0; i < 4; i++) {
-        const float send = b1 ? w8[i] : w8[i + 4];
-        const float keep = b1 ? w8[i + 4] : w8[i];
-        w4[i] = keep + __shfl_xor_sync(0xffffffffu, send, 2);
+        const float send = b0 ? w8[i] : w8[i + 4];
+        const float keep = b0 ? w8[i + 4] : w8[i];
+        w4[i] = keep + __shfl_xor_sync(0xffffffffu, send, 1);
     }
-#pragma unroll
-    for (int i = 0; i < 2; i++) {
-        const float send = b0 ? w4[i] : w4[i + 2];
-        const float keep = b0 ? w4[i + 2] : w4[i];
-        w2[i] = keep + __shfl_xor_sync(0xffffffffu, send, 1);
-    }
-    return make_float2(w2[0], w2[1]);   // components (8*b2 + 4*b1 + 2*b0) + {0, 1} = 2*(lane&7) + {0, 1}
+    return make_float4(w4[0], w4[1], w4[2], w4[3]);   // components 4*(lane&3) + {0,1,2,3}
 }
 
-__global__ void __launch_bounds__(256, 3)
+struct GhBwdPix {
+    float T, A, last_alpha, last_cdot, T_final, bg_dot, pyf;
+    uint32_t last;
+    float dL[GH_NUM_CHANNELS];
+};
+
+// One pixel's share of one Gaussian, branch-free: every lane runs the same instruction stream and a
+// pixel that does not blend this Gaussian (behind its last contributor, power > 0, alpha < 1/255 --
+// the reference's three `continue`s, backward.cu:490-505) contributes exact zeros and keeps its state.
+// FIRST = true assigns v, false accumulates into it (the two pixels of a lane are summed in registers).
+template <bool FIRST>
+__device__ __forceinline__ bool gh_bwd_pixel(GhBwdPix& p, const float4 g0, const float4 g1, const float2* feat,
+                                             float pxf, uint32_t pos, float ddelx_dx, float ddely_dy, float (&v)[16]) {
+    const float dx = GH_SUB(g0.x, pxf), dy = GH_SUB(g0.y, p.pyf);
+    const float power = gh_power(dx, dy, g0.z, g0.w, g1.x);
+    const float Gx = expf((power > 0.0f) ? 0.0f : power);      // expf(power) whenever the reference evaluates it
+    const float alpha = fminf(0.99f, GH_MUL(g1.y, Gx));
+    const bool ok = (pos < p.last) & !(power > 0.0f) & !(alpha < 1.0f / 255.0f);
+    const float am = ok ? alpha : 0.f;
+    const float G = ok ? Gx : 0.f;
+    // T_{before this Gaussian} = T / (1 - alpha); gradients only need ~1 ulp here, so one fast reciprocal
+    const float r = __fdividef(1.0f, 1.0f - am);              // exactly 1 when am == 0
+    p.T *= r;
+    const float w = am * p.T;                                  // d(out)/d(color)
+    float cdot = 0.f;
+#pragma unroll
+    for (int k = 0; k < GH_HALF_C; k++) {
+        const float2 f = feat[k];
+        cdot = fmaf(f.x, p.dL[2 * k], cdot);
+        cdot = fmaf(f.y, p.dL[2 * k + 1], cdot);
+        if (FIRST) {
+            v[2 * k] = w * p.dL[2 * k];
+            v[2 * k + 1] = w * p.dL[2 * k + 1];
+        } else {
+            v[2 * k] = fmaf(w, p.dL[2 * k], v[2 * k]);
+            v[2 * k + 1] = fmaf(w, p.dL[2 * k + 1], v[2 * k + 1]);
+        }
+    }
+    // suffix recursion on the dot product (backward.cu:519-523), state advances only when blended
+    const float A_new = fmaf(p.last_alpha, p.last_cdot, (1.f - p.last_alpha) * p.A);
+    // alpha also scales how much background shows through (backward.cu:535-538)
+    float dL_dalpha = fmaf(cdot - A_new, p.T, (-p.T_final * r) * p.bg_dot);
+    dL_dalpha = ok ? dL_dalpha : 0.f;
+    p.A = ok ? A_new : p.A;
+    p.last_cdot = ok ? cdot : p.last_cdot;
+    p.last_alpha = ok ? alpha : p.last_alpha;
+    const float dL_dG = g1.y * dL_dalpha;
+    const float gdx = G * dx, gdy = G * dy;
+    const float dG_ddelx = -gdx * g0.z - gdy * g0.w;
+    const float dG_ddely = -gdy * g1.x - gdx * g0.w;
+    const float t10 = dL_dG * dG_ddelx * ddelx_dx, t11 = dL_dG * dG_ddely * ddely_dy;
+    const float hg = -0.5f * dL_dG;
+    const float t12 = hg * gdx * dx, t13 = hg * gdx * dy, t14 = hg * gdy * dy, t15 = G * dL_dalpha;
+    if (FIRST) { v[10] = t10; v[11] = t11; v[12] = t12; v[13] = t13; v[14] = t14; v[15] = t15; }
+    else { v[10] += t10; v[11] += t11; v[12] += t12; v[13] += t13; v[14] += t14; v[15] += t15; }
+    return ok;
+}
+
+__global__ void __launch_bounds__(GH_BWD_THREADS, 4)
 gh_blend_backward_kernel(const uint2* __restrict__ ranges, const uint64_t* __restrict__ inst,
                          const GhGeo* __restrict__ geo, const float* __restrict__ features,
                          int W, int H, int gx, const float* __restrict__ bg,
@@ -337,61 +394,71 @@ gh_blend_backward_kernel(const uint2* __restrict__ ranges, const uint64_t* __res
                          float* __restrict__ acc16)   // [P][16]: colors 0..9, mean2D x,y, conic x,y,w, opacity
 {
     __shared__ GhStage st;
-    __shared__ uint32_t s_warp_last[8];
+    __shared__ uint32_t s_warp_last[GH_BWD_THREADS / 32];
 
     const int tile = blockIdx.x;
     const int tx = tile % gx, ty = tile / gx;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int blk = 4 * warp + (lane >> 3);
-    const int px = tx * GH_BLOCK_X + 4 * (lane >> 3) + (lane & 3);
-    const int py = ty * GH_BLOCK_Y + 2 * warp + ((lane >> 2) & 1);
-    const bool inside = (px < W) && (py < H);
-    const float pxf = (float)px, pyf = (float)py;
+    const int blk = 8 * warp + (lane >> 2);           // block = 4 lanes; bx = blk & 3, by = blk >> 2
+    const int px = tx * GH_BLOCK_X + 4 * (blk & 3) + (lane & 3);
+    const int py0 = ty * GH_BLOCK_Y + 2 * (blk >> 2);
+    const float pxf = (float)px;
     const float tx0 = (float)(tx * GH_BLOCK_X), ty0 = (float)(ty * GH_BLOCK_Y);
-    const unsigned gshift = lane & 24;
-    const size_t pix = (size_t)py * W + px;
+    const unsigned gshift = lane & 28;
     const size_t plane = (size_t)H * W;
-
     const uint2 rg = ranges[tile];
 
-    const float T_final = inside ? final_T[pix] : 0.f;
-    float T = T_final;
-    const uint32_t last = inside ? n_contrib[pix] : 0u;   // pixel blends list positions 1..last
-
-    float dL_dpixel[GH_NUM_CHANNELS];
-    float bg_dot_dpixel = 0.f;
+    GhBwdPix pix[2];
 #pragma unroll
-    for (int ch = 0; ch < GH_NUM_CHANNELS; ch++) {
-        dL_dpixel[ch] = inside ? dL_dpix[ch * plane + pix] : 0.f;
-        bg_dot_dpixel += __ldg(bg + ch) * dL_dpixel[ch];
+    for (int r = 0; r < 2; r++) {
+        const int py = py0 + r;
+        const bool inside = (px < W) && (py < H);
+        const size_t pi = (size_t)py * W + px;
+        pix[r].pyf = (float)py;
+        pix[r].T_final = inside ? final_T[pi] : 0.f;
+        pix[r].T = pix[r].T_final;
+        pix[r].last = inside ? n_contrib[pi] : 0u;     // pixel blends list positions 1..last
+        pix[r].A = 0.f; pix[r].last_alpha = 0.f; pix[r].last_cdot = 0.f;
+        float bgd = 0.f;
+#pragma unroll
+        for (int ch = 0; ch < GH_NUM_CHANNELS; ch++) {
+            pix[r].dL[ch] = inside ? dL_dpix[ch * plane + pi] : 0.f;
+            bgd += __ldg(bg + ch) * pix[r].dL[ch];
+        }
+        pix[r].bg_dot = bgd;
     }
-    float A = 0.f, last_alpha = 0.f, last_cdot = 0.f;
-
     // pixel-coordinate -> NDC chain rule factors (backward.cu:464-465)
     const float ddelx_dx = 0.5f * W, ddely_dy = 0.5f * H;
 
-    // how far does this quarter warp / warp / tile reach into the list?
-    uint32_t glast = last;
-    glast = max(glast, __shfl_xor_sync(0xffffffffu, glast, 4));
+    // how far does this block / warp / tile reach into the list?
+    uint32_t glast = max(pix[0].last, pix[1].last);
     glast = max(glast, __shfl_xor_sync(0xffffffffu, glast, 2));
     glast = max(glast, __shfl_xor_sync(0xffffffffu, glast, 1));
-    uint32_t wlast = max(glast, __shfl_xor_sync(0xffffffffu, glast, 8));
-    wlast = max(wlast, __shfl_xor_sync(0xffffffffu, wlast, 16));
+    uint32_t wlast = glast;
+#pragma unroll
+    for (int o = 4; o < 32; o <<= 1) wlast = max(wlast, __shfl_xor_sync(0xffffffffu, wlast, o));
     if (lane == 0) s_warp_last[warp] = wlast;
     __syncthreads();
     uint32_t tile_last = 0;
 #pragma unroll
-    for (int w = 0; w < 8; w++) tile_last = max(tile_last, s_warp_last[w]);
+    for (int w = 0; w < GH_BWD_THREADS / 32; w++) tile_last = max(tile_last, s_warp_last[w]);
     const int n = (int)tile_last;             // nothing beyond is blended by any pixel of this tile
     const int nchunks = (n + GH_CHUNK - 1) / GH_CHUNK;
 
-    // chunks are visited last to first; prologue stages the last chunk
-    uint32_t next_id = 0;
+    // chunks are visited last to first; every thread stages 2 instances; prologue stages the last chunk
+    uint32_t next_id[2] = {0u, 0u};
     if (nchunks > 0) {
         const int b0 = (nchunks - 1) * GH_CHUNK;
-        if (b0 + tid < n) gh_stage_issue(st, (nchunks - 1) & 1, tid, (uint32_t)inst[(size_t)rg.x + b0 + tid], geo, features);
+#pragma unroll
+        for (int h = 0; h < 2; h++) {
+            const int slot = tid + h * GH_BWD_THREADS;
+            if (b0 + slot < n) gh_stage_issue(st, (nchunks - 1) & 1, slot, (uint32_t)inst[(size_t)rg.x + b0 + slot], geo, features);
+        }
         gh_cp_async_commit();
-        if (nchunks > 1) next_id = (uint32_t)inst[(size_t)rg.x + b0 - GH_CHUNK + tid];
+        if (nchunks > 1) {
+#pragma unroll
+            for (int h = 0; h < 2; h++) next_id[h] = (uint32_t)inst[(size_t)rg.x + b0 - GH_CHUNK + tid + h * GH_BWD_THREADS];
+        }
     }
 
     for (int c = nchunks - 1; c >= 0; c--) {
@@ -401,11 +468,18 @@ gh_blend_backward_kernel(const uint2* __restrict__ ranges, const uint64_t* __res
         gh_cp_async_wait_all();
         __syncthreads();
         if (c > 0) {
-            gh_stage_issue(st, buf ^ 1, tid, next_id, geo, features);   // earlier chunks are always full
+#pragma unroll
+            for (int h = 0; h < 2; h++) gh_stage_issue(st, buf ^ 1, tid + h * GH_BWD_THREADS, next_id[h], geo, features);
             gh_cp_async_commit();
-            if (c > 1) next_id = (uint32_t)inst[(size_t)rg.x + base - 2 * GH_CHUNK + tid];
+            if (c > 1) {
+#pragma unroll
+                for (int h = 0; h < 2; h++)
+                    next_id[h] = (uint32_t)inst[(size_t)rg.x + base - 2 * GH_CHUNK + tid + h * GH_BWD_THREADS];
+            }
         }
+        // per-block lists: each of the 4 warps scan-converts two batches of 32 Gaussians
         gh_build_lists(st, buf, cnt, warp, lane, tx0, ty0);
+        gh_build_lists(st, buf, cnt, warp + 4, lane, tx0, ty0);
         __syncthreads();
         if ((uint32_t)base >= wlast) continue;
 
@@ -414,7 +488,7 @@ gh_blend_backward_kernel(const uint2* __restrict__ ranges, const uint64_t* __res
         while (true) {
             while (cur == 0 && wi > 0) {
                 wi--;
-                // only list positions < glast can have been blended by a pixel of this quarter warp
+                // only list positions < glast can have been blended by a pixel of this block
                 const int lim = (int)glast - (base + wi * 32);
                 const uint32_t valid = lim >= 32 ? 0xffffffffu : (lim <= 0 ? 0u : ((1u << lim) - 1u));
                 cur = st.bits[blk][wi] & valid;
@@ -422,61 +496,24 @@ gh_blend_backward_kernel(const uint2* __restrict__ ranges, const uint64_t* __res
             const bool act = (cur != 0);
             if (!__any_sync(0xffffffffu, act)) break;
 
+            // blocks whose list is exhausted run the same code on slot 0 with pos = UINT_MAX (-> all zeros)
+            const int bpos = act ? 31 - __clz(cur) : 0;   // back to front
+            cur &= ~(1u << bpos);
+            const int jj = act ? wi * 32 + bpos : 0;
+            const uint32_t id = st.id[buf][jj];
+            const float4 g0 = st.g0[buf][jj], g1 = st.g1[buf][jj];
+            const float2* feat = &st.feat[buf][jj * GH_HALF_C];
+            const uint32_t pos = act ? (uint32_t)(base + jj) : 0xffffffffu;
             float v[16];
-#pragma unroll
-            for (int k = 0; k < 16; k++) v[k] = 0.f;
-            bool contrib = false;
-            uint32_t id = 0;
-            if (act) {
-                const int bpos = 31 - __clz(cur);   // back to front
-                cur &= ~(1u << bpos);
-                const int jj = wi * 32 + bpos;
-                id = st.id[buf][jj];
-                // reference: contributor--; if (contributor >= last_contributor) continue;
-                if ((uint32_t)(base + jj) < last) {
-                    const float4 g0 = st.g0[buf][jj], g1 = st.g1[buf][jj];
-                    const GhPixEval e = gh_eval(g0, g1, pxf, pyf);
-                    if (e.ok) {
-                        contrib = true;
-                        const float alpha = e.alpha, G = e.G;
-                        T = GH_DIV(T, GH_SUB(1.0f, alpha));
-                        const float dchannel_dcolor = alpha * T;
-                        float cdot = 0.f;
-#pragma unroll
-                        for (int k = 0; k < GH_HALF_C; k++) {
-                            const float2 f = st.feat[buf][jj * GH_HALF_C + k];
-                            cdot = fmaf(f.x, dL_dpixel[2 * k], cdot);
-                            cdot = fmaf(f.y, dL_dpixel[2 * k + 1], cdot);
-                            v[2 * k] = dchannel_dcolor * dL_dpixel[2 * k];
-                            v[2 * k + 1] = dchannel_dcolor * dL_dpixel[2 * k + 1];
-                        }
-                        // suffix recursion on the dot product (backward.cu:519-523)
-                        A = fmaf(last_alpha, last_cdot, (1.f - last_alpha) * A);
-                        last_cdot = cdot;
-                        float dL_dalpha = (cdot - A) * T;
-                        last_alpha = alpha;
-                        // alpha also scales how much background shows through (backward.cu:535-538)
-                        dL_dalpha += (-T_final / (1.f - alpha)) * bg_dot_dpixel;
-
-                        const float dL_dG = g1.y * dL_dalpha;
-                        const float gdx = G * e.dx, gdy = G * e.dy;
-                        const float dG_ddelx = -gdx * g0.z - gdy * g0.w;
-                        const float dG_ddely = -gdy * g1.x - gdx * g0.w;
-                        v[10] = dL_dG * dG_ddelx * ddelx_dx;
-                        v[11] = dL_dG * dG_ddely * ddely_dy;
-                        v[12] = -0.5f * gdx * e.dx * dL_dG;
-                        v[13] = -0.5f * gdx * e.dy * dL_dG;
-                        v[14] = -0.5f * gdy * e.dy * dL_dG;
-                        v[15] = G * dL_dalpha;
-                    }
-                }
-            }
+            const bool c0 = gh_bwd_pixel<true>(pix[0], g0, g1, feat, pxf, pos, ddelx_dx, ddely_dy, v);
+            const bool c1 = gh_bwd_pixel<false>(pix[1], g0, g1, feat, pxf, pos, ddelx_dx, ddely_dy, v);
+            const bool contrib = c0 | c1;
             const uint32_t cm = __ballot_sync(0xffffffffu, contrib);
             if (cm == 0u) continue;
-            const float2 s = gh_group_reduce16(v, lane);
-            if ((cm >> gshift) & 0xffu) {
-                float2* dst = reinterpret_cast<float2*>(acc16 + (size_t)id * 16) + (lane & 7);
-                atomicAdd(dst, s);    // REDG.E.ADD.F32x2
+            const float4 s = gh_group4_reduce16(v, lane);
+            if ((cm >> gshift) & 0xfu) {
+                float4* dst = reinterpret_cast<float4*>(acc16 + (size_t)id * 16) + (lane & 3);
+                atomicAdd(dst, s);    // REDG.E.ADD.F32x4
             }
         }
     }
@@ -517,7 +554,7 @@ void gh_launch_blend_backward(int W, int H, int gx, int gy, GhGeomWS geom, GhImg
                               const float* features, const float* bg, const float* dL_dpix,
                               cudaStream_t stream)
 {
-    gh_blend_backward_kernel<<<gx * gy, 256, 0, stream>>>(img.ranges, bin.inst, geom.geo, features,
+    gh_blend_backward_kernel<<<gx * gy, GH_BWD_THREADS, 0, stream>>>(img.ranges, bin.inst, geom.geo, features,
                                                           W, H, gx, bg, img.final_T, img.n_contrib, dL_dpix,
                                                           geom.acc16);
 }
