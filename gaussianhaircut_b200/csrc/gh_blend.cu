@@ -165,39 +165,58 @@ __device__ __forceinline__ void gh_build_pixel_lists(const GhStage& st, uint32_t
     uint32_t rowmask[16];
 #pragma unroll
     for (int r = 0; r < 16; r++) rowmask[r] = 0u;
+    float gx = 0.f, gy = 0.f, b = 0.f, ia = 0.f, aQ = -1.f, bbac = 0.f;
+    int r0 = 16, r1 = -1;            // rows of the tile this Gaussian can reach
+    bool all_pixels = false;
     if (j < cnt) {
         const float4 g0 = st.g0[buf][j], g1 = st.g1[buf][j];
-        const float gx = g0.x, gy = g0.y, a = g0.z, b = g0.w, c = g1.x, thr = g1.z, pd = g1.w;
+        gx = g0.x; gy = g0.y; b = g0.w;
+        const float a = g0.z, c = g1.x, thr = g1.z, pd = g1.w;
         const float mxd = fmaxf(fabsf(gx - tx0), fabsf(gx - (tx0 + 15.f)));
         const float myd = fmaxf(fabsf(gy - ty0), fabsf(gy - (ty0 + 15.f)));
         const float slack = 1e-3f + 2e-5f * (a * mxd * mxd + c * myd * myd + 2.f * fabsf(b) * mxd * myd);
         const float Q = 2.f * (thr + slack);
         if (pd == 0.f || Q != Q) {
-#pragma unroll
-            for (int r = 0; r < 16; r++) rowmask[r] = 0xffffu;     // no bound available: every pixel
+            all_pixels = true; r0 = 0; r1 = 15;                     // no bound available: every pixel
         } else if (Q >= 0.f) {
-            const float ia = __frcp_rn(a);
-            const float aQ = a * Q;
-            const float bbac = b * b - a * c;                      // < 0 for a PD conic
+            ia = __frcp_rn(a);
+            aQ = a * Q;
+            bbac = b * b - a * c;                                   // < 0 for a PD conic
+            // rows with a real span: dy^2 < aQ / (ac - b^2)
+            const float ry = sqrtf(aQ / (-bbac)) + 0.01f;
+            r0 = 0; r1 = 15;
+            if (ry == ry) { r0 = max(0, __float2int_ru(gy - ry - ty0)); r1 = min(15, __float2int_rd(gy + ry - ty0)); }
+        }
+    }
+    // warp-uniform row window: the 32 Gaussians of a warp are neighbours in depth, not in space, but
+    // strand Gaussians are small, so most rows are empty for the whole warp
+    int wr0 = r0, wr1 = r1;
 #pragma unroll
-            for (int r = 0; r < 16; r++) {
-                const float dy = gy - (ty0 + (float)r);
-                // a dx^2 + 2 b dy dx + (c dy^2 - Q) <= 0,  dx = gx - px
-                const float disc = fmaf(dy * dy, bbac, aQ);
-                if (disc > 0.f) {
-                    const float sq = disc * rsqrtf(disc);
-                    const float hb = b * dy;
-                    const float lo = (gx + (hb - sq) * ia - 0.01f) - tx0, hi = (gx + (hb + sq) * ia + 0.01f) - tx0;
-                    const int p0 = max(0, __float2int_ru(lo)), p1 = min(15, __float2int_rd(hi));
-                    if (p0 <= p1) rowmask[r] = ((2u << (p1 - p0)) - 1u) << p0;
-                }
-            }
+    for (int o = 16; o > 0; o >>= 1) {
+        wr0 = min(wr0, __shfl_xor_sync(0xffffffffu, wr0, o));
+        wr1 = max(wr1, __shfl_xor_sync(0xffffffffu, wr1, o));
+    }
+#pragma unroll
+    for (int r = 0; r < 16; r++) {
+        if (r < wr0 || r > wr1) continue;                           // uniform
+        if (all_pixels) { rowmask[r] = 0xffffu; continue; }
+        const float dy = gy - (ty0 + (float)r);
+        // a dx^2 + 2 b dy dx + (c dy^2 - Q) <= 0,  dx = gx - px
+        const float disc = fmaf(dy * dy, bbac, aQ);
+        if (disc > 0.f) {
+            const float sq = disc * rsqrtf(disc);
+            const float hb = b * dy;
+            const float lo = (gx + (hb - sq) * ia - 0.01f) - tx0, hi = (gx + (hb + sq) * ia + 0.01f) - tx0;
+            const int p0 = max(0, __float2int_ru(lo)), p1 = min(15, __float2int_rd(hi));
+            if (p0 <= p1) rowmask[r] = ((2u << (p1 - p0)) - 1u) << p0;
         }
     }
 #pragma unroll
     for (int t = 0; t < 8; t++) {
         const uint32_t word = rowmask[2 * t] | (rowmask[2 * t + 1] << 16);   // my coverage of warp t's pixels
-        pixbits[warp * 256 + t * 32 + lane] = gh_transpose32(word, lane);    // pixel 32t+lane: bits = Gaussians
+        uint32_t col = 0u;
+        if (__any_sync(0xffffffffu, word != 0u)) col = gh_transpose32(word, lane);
+        pixbits[warp * 256 + t * 32 + lane] = col;                           // pixel 32t+lane: bits = Gaussians
     }
 }
 
@@ -262,11 +281,19 @@ gh_blend_forward_kernel(const uint2* __restrict__ ranges, const uint64_t* __rest
         __syncthreads();
 
         if (!done) {
+            // which of my pixel's 8 list words are non-empty
+            uint32_t nz = 0u;
+#pragma unroll
+            for (int k = 0; k < GH_CHUNK / 32; k++) nz |= (pixbits[k * 256 + tid] != 0u) ? (1u << k) : 0u;
             int wi = 0;
-            uint32_t cur = pixbits[tid];
+            uint32_t cur = 0u;
             while (true) {
-                while (cur == 0u && wi < GH_CHUNK / 32 - 1) { wi++; cur = pixbits[wi * 256 + tid]; }
-                if (cur == 0u) break;
+                if (cur == 0u) {
+                    if (nz == 0u) break;
+                    wi = __ffs(nz) - 1;
+                    nz &= nz - 1;
+                    cur = pixbits[wi * 256 + tid];
+                }
                 const int bpos = __ffs(cur) - 1;
                 cur &= cur - 1;
                 const int jj = wi * 32 + bpos;
