@@ -221,7 +221,7 @@ __device__ __forceinline__ void gh_build_pixel_lists(const GhStage& st, uint32_t
 }
 
 // ------------------------------------------------------------------------------------------ forward
-__global__ void __launch_bounds__(256, 3)
+__global__ void __launch_bounds__(256, 4)
 gh_blend_forward_kernel(const uint2* __restrict__ ranges, const uint64_t* __restrict__ inst,
                         const GhGeo* __restrict__ geo, const float* __restrict__ features,
                         int W, int H, int gx, const float* __restrict__ bg,
@@ -573,6 +573,8 @@ void gh_launch_blend_forward(int W, int H, int gx, int gy, GhGeomWS geom, GhImgW
                              const float* features, const float* bg, float* out_color,
                              cudaStream_t stream)
 {
+    // ask for the largest shared-memory carve-out so that 4 CTAs (4 x 48 KB) are resident per SM
+    cudaFuncSetAttribute(gh_blend_forward_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
     gh_blend_forward_kernel<<<gx * gy, 256, 0, stream>>>(img.ranges, bin.inst, geom.geo, features,
                                                          W, H, gx, bg, img.final_T, img.n_contrib, out_color);
 }
@@ -581,6 +583,7 @@ void gh_launch_blend_backward(int W, int H, int gx, int gy, GhGeomWS geom, GhImg
                               const float* features, const float* bg, const float* dL_dpix,
                               cudaStream_t stream)
 {
+    cudaFuncSetAttribute(gh_blend_backward_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
     gh_blend_backward_kernel<<<gx * gy, GH_BWD_THREADS, 0, stream>>>(img.ranges, bin.inst, geom.geo, features,
                                                           W, H, gx, bg, img.final_T, img.n_contrib, dL_dpix,
                                                           geom.acc16);
