@@ -170,7 +170,6 @@ int gh_forward_preprocess(
         g_launches += 1;
     }
     GH_STAGE(stream, debug, "tile scan");
-
     GhCtrl h;
     e = cudaMemcpyAsync(&h, img.ctrl, sizeof(GhCtrl), cudaMemcpyDeviceToHost, stream);
     if (e == cudaSuccess) e = cudaStreamSynchronize(stream);
@@ -264,15 +263,19 @@ int gh_backward(
         cudaError_t e = cudaMemsetAsync(geom.acc16, 0, (size_t)P * 64, stream);
         if (e != cudaSuccess) return gh_check_cuda(e, "memset(accumulation records)");
         gh_launch_blend_backward(width, height, gx, gy, geom, img, bin, colors_precomp, background, dL_dpix, stream);
-        gh_launch_unpack_grads(P, geom, dL_dmean2D, dL_dconic, dL_dopacity, dL_dcolor, stream);
-        g_launches += 2;
+        g_launches += 1;
+        if (conic_precomp != nullptr) {   // otherwise the geometry backward unpacks the records itself
+            gh_launch_unpack_grads(P, geom, dL_dmean2D, dL_dconic, dL_dopacity, dL_dcolor, stream);
+            g_launches += 1;
+        }
     }
     GH_STAGE(stream, debug, "blend backward");
-    if (conic_precomp == nullptr) {   // reference: geometry backward is a no-op when the conic was supplied
+    if (conic_precomp == nullptr && R > 0) {   // reference: geometry backward is a no-op when the conic was supplied
         GhStageTimer t(GH_ST_PREPROCESS_BWD, stream);
         gh_launch_preprocess_backward(P, means3D, radii, scales, scale_modifier, rotations, cov3D_precomp,
                                       conic_precomp, viewmatrix, projmatrix, width, height, tan_fovx, tan_fovy,
-                                      dL_dmean2D, dL_dconic, dL_dmean3D, dL_dcov3D, dL_dscale, dL_drot, stream);
+                                      geom.acc16, dL_dmean2D, dL_dconic, dL_dopacity, dL_dcolor,
+                                      dL_dmean3D, dL_dcov3D, dL_dscale, dL_drot, stream);
         g_launches += 1;
     }
     GH_STAGE(stream, debug, "preprocess backward");

@@ -21,54 +21,71 @@ __global__ void __launch_bounds__(1024)
 gh_tile_scan_kernel(int T, const uint32_t* __restrict__ tile_count, uint32_t* __restrict__ tile_cursor,
                     uint2* __restrict__ ranges, GhCtrl* __restrict__ ctrl)
 {
-    __shared__ uint32_t warp_sums[32];
+    // each thread owns 8 consecutive tiles per round: one block scan per 8192 tiles
+    __shared__ uint32_t warp_sums[32], warp_max[32];
     __shared__ uint32_t carry_s;
-    __shared__ uint32_t max_s[32];
     const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
     if (tid == 0) carry_s = 0;
-    uint32_t local_max = 0;
+    uint32_t tmax = 0;
     __syncthreads();
-    for (int base = 0; base < T; base += 1024) {
-        const int i = base + tid;
-        const uint32_t c = (i < T) ? tile_count[i] : 0u;
-        local_max = max(local_max, c);
-        uint32_t v = c;   // inclusive warp scan
+    for (int base = 0; base < T; base += 8192) {
+        const int i0 = base + tid * 8;
+        uint32_t c[8];
+        uint32_t sum = 0;
 #pragma unroll
-        for (int o = 1; o < 32; o <<= 1) {
-            const uint32_t n = __shfl_up_sync(0xffffffffu, v, o);
-            if (lane >= o) v += n;
+        for (int k = 0; k < 8; k++) c[k] = 0u;
+        if (i0 + 8 <= T) {     // 32-byte aligned: two 128-bit loads
+            const uint4 a = reinterpret_cast<const uint4*>(tile_count + i0)[0], b = reinterpret_cast<const uint4*>(tile_count + i0)[1];
+            c[0] = a.x; c[1] = a.y; c[2] = a.z; c[3] = a.w; c[4] = b.x; c[5] = b.y; c[6] = b.z; c[7] = b.w;
+        } else {
+            for (int k = 0; k < 8; k++) if (i0 + k < T) c[k] = tile_count[i0 + k];
         }
+#pragma unroll
+        for (int k = 0; k < 8; k++) { sum += c[k]; tmax = max(tmax, c[k]); }
+        uint32_t v = sum;   // inclusive warp scan
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) { const uint32_t nb = __shfl_up_sync(0xffffffffu, v, o); if (lane >= o) v += nb; }
         if (lane == 31) warp_sums[wid] = v;
         __syncthreads();
         if (wid == 0) {
             uint32_t w = warp_sums[lane];
 #pragma unroll
-            for (int o = 1; o < 32; o <<= 1) {
-                const uint32_t n = __shfl_up_sync(0xffffffffu, w, o);
-                if (lane >= o) w += n;
-            }
+            for (int o = 1; o < 32; o <<= 1) { const uint32_t nb = __shfl_up_sync(0xffffffffu, w, o); if (lane >= o) w += nb; }
             warp_sums[lane] = w;   // inclusive over warps
         }
         __syncthreads();
         const uint32_t carry = carry_s;
-        const uint32_t incl = carry + v + (wid > 0 ? warp_sums[wid - 1] : 0u);
-        const uint32_t excl = incl - c;
-        if (i < T) {
-            tile_cursor[i] = excl;
+        uint32_t run = carry + (v - sum) + (wid > 0 ? warp_sums[wid - 1] : 0u);
+        uint32_t cur8[8];
+        uint2 rg8[8];
+#pragma unroll
+        for (int k = 0; k < 8; k++) {
+            cur8[k] = run;
             // empty tiles keep (0,0) like the reference's memset + identifyTileRanges
-            ranges[i] = (c > 0) ? make_uint2(excl, incl) : make_uint2(0u, 0u);
+            rg8[k] = (c[k] > 0) ? make_uint2(run, run + c[k]) : make_uint2(0u, 0u);
+            run += c[k];
+        }
+        if (i0 + 8 <= T) {
+            uint4* cp = reinterpret_cast<uint4*>(tile_cursor + i0);
+            cp[0] = make_uint4(cur8[0], cur8[1], cur8[2], cur8[3]);
+            cp[1] = make_uint4(cur8[4], cur8[5], cur8[6], cur8[7]);
+            uint4* rp = reinterpret_cast<uint4*>(ranges + i0);
+#pragma unroll
+            for (int k = 0; k < 4; k++) rp[k] = make_uint4(rg8[2 * k].x, rg8[2 * k].y, rg8[2 * k + 1].x, rg8[2 * k + 1].y);
+        } else {
+            for (int k = 0; k < 8; k++) if (i0 + k < T) { tile_cursor[i0 + k] = cur8[k]; ranges[i0 + k] = rg8[k]; }
         }
         __syncthreads();
-        if (tid == 1023) carry_s = incl;
+        if (tid == 1023) carry_s = run;
         __syncthreads();
     }
 #pragma unroll
-    for (int o = 16; o > 0; o >>= 1) local_max = max(local_max, __shfl_xor_sync(0xffffffffu, local_max, o));
-    if (lane == 0) max_s[wid] = local_max;
+    for (int o = 16; o > 0; o >>= 1) tmax = max(tmax, __shfl_xor_sync(0xffffffffu, tmax, o));
+    if (lane == 0) warp_max[wid] = tmax;
     __syncthreads();
     if (tid == 0) {
         uint32_t m = 0;
-        for (int w = 0; w < 32; w++) m = max(m, max_s[w]);
+        for (int w = 0; w < 32; w++) m = max(m, warp_max[w]);
         ctrl->num_rendered = carry_s;
         ctrl->max_tile_len = m;
     }
@@ -116,70 +133,7 @@ gh_emit_kernel(int P, const int* __restrict__ radii, const GhGeo* __restrict__ g
     }
 }
 
-// ---------------------------------------------------------------- per-tile sort
-// Normalised bitonic network (every comparator puts the smaller key at the lower index), so
-// elements beyond n behave as +inf without being materialised: a comparator whose upper index
-// is >= n is simply skipped.
-__device__ __forceinline__ void gh_ce(uint64_t& a, uint64_t& b) {
-    const uint64_t lo = a < b ? a : b, hi = a < b ? b : a;
-    a = lo; b = hi;
-}
-
-template <typename KeyPtr>
-__device__ __forceinline__ void gh_bitonic_sort(KeyPtr keys, const uint32_t n, const int tid, const int nt)
-{
-    const uint64_t INF = ~0ull;             // virtual padding: never stored, never moves
-    uint32_t ln2 = 0;                       // n2 = 1 << ln2 >= n
-    while ((1u << ln2) < n) ln2++;
-    const uint32_t half = (1u << ln2) >> 1, quarter = half >> 1;
-    for (uint32_t lk = 1; lk <= ln2; lk++) {      // merge blocks of size k = 1 << lk
-        {   // first step of the merge: partner = mirror inside the block of size k
-            const uint32_t k = 1u << lk, hk = k >> 1;
-            for (uint32_t t = tid; t < half; t += nt) {
-                const uint32_t blk = t >> (lk - 1), off = t & (hk - 1);
-                const uint32_t i = (blk << lk) + off, j = (blk << lk) + (k - 1 - off);
-                if (j < n) {
-                    const uint64_t a = keys[i], b = keys[j];
-                    if (a > b) { keys[i] = b; keys[j] = a; }
-                }
-            }
-            __syncthreads();
-        }
-        int ls = (int)lk - 2;                      // remaining strides s = k/4 ... 1
-        // two strides (s, s/2) per pass: a thread owns i, i+s/2, i+s, i+3s/2 and does 4 exchanges in registers
-        for (; ls >= 1; ls -= 2) {
-            const uint32_t sft = (uint32_t)ls, s = 1u << sft, h = s >> 1;
-            for (uint32_t t = tid; t < quarter; t += nt) {
-                const uint32_t i = ((t >> (sft - 1)) << (sft + 1)) | (t & (h - 1));
-                if (i < n) {
-                    const uint32_t ib = i + h, ic = i + s, id = ic + h;
-                    uint64_t ka = keys[i];
-                    uint64_t kb = ib < n ? keys[ib] : INF;
-                    uint64_t kc = ic < n ? keys[ic] : INF;
-                    uint64_t kd = id < n ? keys[id] : INF;
-                    gh_ce(ka, kc); gh_ce(kb, kd);
-                    gh_ce(ka, kb); gh_ce(kc, kd);
-                    keys[i] = ka;
-                    if (ib < n) keys[ib] = kb;
-                    if (ic < n) keys[ic] = kc;
-                    if (id < n) keys[id] = kd;
-                }
-            }
-            __syncthreads();
-        }
-        if (ls == 0) {                             // odd number of strides left: the stride-1 stage
-            for (uint32_t t = tid; t < half; t += nt) {
-                const uint32_t i = t << 1, j = i + 1;
-                if (j < n) {
-                    const uint64_t a = keys[i], b = keys[j];
-                    if (a > b) { keys[i] = b; keys[j] = a; }
-                }
-            }
-            __syncthreads();
-        }
-    }
-}
-
+// ---------------------------------------------------------------- per-tile sort (network in gh_common.cuh)
 // SMEM_KEYS: capacity of the shared staging buffer; handles tiles with lo < n <= hi.
 // Tiles longer than the buffer are sorted in place in global memory by the same network.
 template <int NT>
@@ -220,15 +174,15 @@ void gh_launch_emit(int P, const int* radii, GhGeomWS geom, GhImgWS img, GhBinWS
 
 int gh_launch_tile_sort(int T, unsigned int max_tile_len, GhImgWS img, GhBinWS bin, cudaStream_t stream)
 {
-    if (max_tile_len < 2) return 0;
-    constexpr uint32_t SMALL = 2048;     // 16 KB of keys, 256 threads
+    // tiles with at most GH_INKERNEL_SORT_MAX instances are sorted by the forward blend CTA itself
+    // (gh_blend.cu); only longer lists need this kernel
+    constexpr uint32_t SMALL = GH_INKERNEL_SORT_MAX;
     constexpr uint32_t LARGE = 24576;    // 192 KB of keys, 1024 threads
-    gh_tile_sort_kernel<256><<<T, 256, SMALL * 8, stream>>>(img.ranges, bin.inst, 0u, SMALL, SMALL);
     if (max_tile_len > SMALL) {
         cudaFuncSetAttribute(gh_tile_sort_kernel<1024>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                              (int)(LARGE * 8));
         gh_tile_sort_kernel<1024><<<T, 1024, LARGE * 8, stream>>>(img.ranges, bin.inst, SMALL, 0xffffffffu, LARGE);
-        return 2;
+        return 1;
     }
-    return 1;
+    return 0;
 }

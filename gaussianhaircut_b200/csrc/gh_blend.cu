@@ -222,7 +222,7 @@ __device__ __forceinline__ void gh_build_pixel_lists(const GhStage& st, uint32_t
 
 // ------------------------------------------------------------------------------------------ forward
 __global__ void __launch_bounds__(256, 4)
-gh_blend_forward_kernel(const uint2* __restrict__ ranges, const uint64_t* __restrict__ inst,
+gh_blend_forward_kernel(const uint2* __restrict__ ranges, uint64_t* inst,
                         const GhGeo* __restrict__ geo, const float* __restrict__ features,
                         int W, int H, int gx, const float* __restrict__ bg,
                         float* __restrict__ final_T, uint32_t* __restrict__ n_contrib,
@@ -255,6 +255,20 @@ gh_blend_forward_kernel(const uint2* __restrict__ ranges, const uint64_t* __rest
     uint32_t last = 0;
     bool done = !inside;
     bool warp_done = (__ballot_sync(0xffffffffu, done) == 0xffffffffu);
+
+    // Sort this tile's bucket by (depth bits, Gaussian index) right here when it fits the staging buffers
+    // (<= 2048 records = 16 KB): the sort is latency/barrier bound, the blend is issue bound, and as
+    // one kernel the two overlap across the CTAs of an SM.  The sorted bucket is written back for the
+    // backward pass.  Longer lists were sorted by gh_tile_sort_kernel before this launch.
+    if (n >= 2 && n <= (int)GH_INKERNEL_SORT_MAX) {
+        uint64_t* skeys = reinterpret_cast<uint64_t*>(&st.g0[0][0]);     // g0 + g1 = 16 KB contiguous
+        uint64_t* gl = inst + rg.x;
+        for (int i = tid; i < n; i += 256) skeys[i] = gl[i];
+        __syncthreads();
+        gh_bitonic_sort(skeys, (uint32_t)n, tid, 256);
+        for (int i = tid; i < n; i += 256) gl[i] = skeys[i];
+        __syncthreads();
+    }
 
     // prologue: chunk 0 in flight, indices of chunk 1 in a register
     uint32_t next_id = 0;

@@ -194,4 +194,70 @@ __device__ __forceinline__ bool gh_cull_hit(const GhGeo& g, float rx0, float rx1
     const bool miss = (0.5f * qmin > g.thr + slack);   // false for NaN
     return inside | (g.pd == 0.f) | !miss;
 }
+
+// ---- per-tile sort network (used by the forward blend CTA for its own list and by gh_tile_sort_kernel)
+#define GH_INKERNEL_SORT_MAX 2048u
+// Normalised bitonic network (every comparator puts the smaller key at the lower index), so
+// elements beyond n behave as +inf without being materialised: a comparator whose upper index
+// is >= n is simply skipped.
+__device__ __forceinline__ void gh_ce(uint64_t& a, uint64_t& b) {
+    const uint64_t lo = a < b ? a : b, hi = a < b ? b : a;
+    a = lo; b = hi;
+}
+
+template <typename KeyPtr>
+__device__ __forceinline__ void gh_bitonic_sort(KeyPtr keys, const uint32_t n, const int tid, const int nt)
+{
+    const uint64_t INF = ~0ull;             // virtual padding: never stored, never moves
+    uint32_t ln2 = 0;                       // n2 = 1 << ln2 >= n
+    while ((1u << ln2) < n) ln2++;
+    const uint32_t half = (1u << ln2) >> 1, quarter = half >> 1;
+    for (uint32_t lk = 1; lk <= ln2; lk++) {      // merge blocks of size k = 1 << lk
+        {   // first step of the merge: partner = mirror inside the block of size k
+            const uint32_t k = 1u << lk, hk = k >> 1;
+            for (uint32_t t = tid; t < half; t += nt) {
+                const uint32_t blk = t >> (lk - 1), off = t & (hk - 1);
+                const uint32_t i = (blk << lk) + off, j = (blk << lk) + (k - 1 - off);
+                if (j < n) {
+                    const uint64_t a = keys[i], b = keys[j];
+                    if (a > b) { keys[i] = b; keys[j] = a; }
+                }
+            }
+            __syncthreads();
+        }
+        int ls = (int)lk - 2;                      // remaining strides s = k/4 ... 1
+        // two strides (s, s/2) per pass: a thread owns i, i+s/2, i+s, i+3s/2 and does 4 exchanges in registers
+        for (; ls >= 1; ls -= 2) {
+            const uint32_t sft = (uint32_t)ls, s = 1u << sft, h = s >> 1;
+            for (uint32_t t = tid; t < quarter; t += nt) {
+                const uint32_t i = ((t >> (sft - 1)) << (sft + 1)) | (t & (h - 1));
+                if (i < n) {
+                    const uint32_t ib = i + h, ic = i + s, id = ic + h;
+                    uint64_t ka = keys[i];
+                    uint64_t kb = ib < n ? keys[ib] : INF;
+                    uint64_t kc = ic < n ? keys[ic] : INF;
+                    uint64_t kd = id < n ? keys[id] : INF;
+                    gh_ce(ka, kc); gh_ce(kb, kd);
+                    gh_ce(ka, kb); gh_ce(kc, kd);
+                    keys[i] = ka;
+                    if (ib < n) keys[ib] = kb;
+                    if (ic < n) keys[ic] = kc;
+                    if (id < n) keys[id] = kd;
+                }
+            }
+            __syncthreads();
+        }
+        if (ls == 0) {                             // odd number of strides left: the stride-1 stage
+            for (uint32_t t = tid; t < half; t += nt) {
+                const uint32_t i = t << 1, j = i + 1;
+                if (j < n) {
+                    const uint64_t a = keys[i], b = keys[j];
+                    if (a > b) { keys[i] = b; keys[j] = a; }
+                }
+            }
+            __syncthreads();
+        }
+    }
+}
+
 #endif  // __CUDACC__

@@ -40,6 +40,7 @@ void gh_launch_preprocess_backward(int P, const float* means3D, const int* radii
                                    const float* cov3D_precomp, const float* conic_precomp,
                                    const float* viewmatrix, const float* projmatrix,
                                    int W, int H, float tan_fovx, float tan_fovy,
-                                   const float* dL_dmean2D, const float* dL_dconic,
+                                   const float* acc16, float* dL_dmean2D, float* dL_dconic,
+                                   float* dL_dopacity, float* dL_dcolor,
                                    float* dL_dmean3D, float* dL_dcov3D, float* dL_dscale, float* dL_drot,
                                    cudaStream_t stream);

@@ -1,5 +1,6 @@
 // Stage 5: backward of the per-Gaussian preprocess, one fused kernel.
 //
+// Also unpacks the blend backward's 64-byte accumulation records into the API gradient tensors.
 // Covers the reference's computeCov2DCUDA (backward.cu:144-274), the projection part of
 // preprocessCUDA (backward.cu:346-400) and the backward of computeCov3D (backward.cu:278-341).
 // When the caller supplied the conic (`conic_precomp`, the mode both reference trainers use) the
@@ -18,13 +19,29 @@ gh_preprocess_backward_kernel(int P, const float* __restrict__ means3D, const in
                               const float* __restrict__ cov3D_precomp,
                               const float* __restrict__ view, const float* __restrict__ proj,
                               float h_x, float h_y, float tan_fovx, float tan_fovy,
-                              const float* __restrict__ dL_dmean2D,   // (P,3), NDC units, z unused
-                              const float* __restrict__ dL_dconic,    // (P,4): .x .y .w used
+                              const float* __restrict__ acc16,        // (P,16) accumulation records of the blend backward
+                              float* __restrict__ dL_dmean2D,         // (P,3), NDC units, z unused      } written here
+                              float* __restrict__ dL_dconic,          // (P,4): .x .y .w used            } from acc16
+                              float* __restrict__ dL_dopacity, float* __restrict__ dL_dcolor,         // }
                               float* __restrict__ dL_dmean3D, float* __restrict__ dL_dcov3D,
                               float* __restrict__ dL_dscale, float* __restrict__ dL_drot)
 {
     const int idx = blockIdx.x * blockDim.x + threadIdx.x;
-    if (idx >= P || !(radii[idx] > 0)) return;
+    if (idx >= P) return;
+    // unpack the 64-byte accumulation record into the reference binding's gradient layouts
+    // (rasterize_points.cu:160-168) -- every row is written, also for Gaussians that were not rendered
+    const float4* rec = reinterpret_cast<const float4*>(acc16 + (size_t)idx * 16);
+    const float4 a0 = rec[0], a1 = rec[1], a2 = rec[2], a3 = rec[3];
+    {
+        float2* dc = reinterpret_cast<float2*>(dL_dcolor + (size_t)idx * GH_NUM_CHANNELS);
+        dc[0] = make_float2(a0.x, a0.y); dc[1] = make_float2(a0.z, a0.w);
+        dc[2] = make_float2(a1.x, a1.y); dc[3] = make_float2(a1.z, a1.w);
+        dc[4] = make_float2(a2.x, a2.y);
+        dL_dmean2D[3 * idx + 0] = a2.z; dL_dmean2D[3 * idx + 1] = a2.w; dL_dmean2D[3 * idx + 2] = 0.f;
+        reinterpret_cast<float4*>(dL_dconic)[idx] = make_float4(a3.x, a3.y, 0.f, a3.z);
+        dL_dopacity[idx] = a3.w;
+    }
+    if (!(radii[idx] > 0)) return;
 
     const float mx = means3D[3 * idx + 0], my = means3D[3 * idx + 1], mz = means3D[3 * idx + 2];
 
@@ -42,7 +59,7 @@ gh_preprocess_backward_kernel(int P, const float* __restrict__ means3D, const in
     }
 
     // ---- computeCov2DCUDA -------------------------------------------------------------------
-    const float dLdcon_x = dL_dconic[4 * idx + 0], dLdcon_y = dL_dconic[4 * idx + 1], dLdcon_z = dL_dconic[4 * idx + 3];
+    const float dLdcon_x = a3.x, dLdcon_y = a3.y, dLdcon_z = a3.z;
     float tx = view[0] * mx + view[4] * my + view[8] * mz + view[12];
     float ty = view[1] * mx + view[5] * my + view[9] * mz + view[13];
     const float tz = view[2] * mx + view[6] * my + view[10] * mz + view[14];
@@ -121,7 +138,7 @@ gh_preprocess_backward_kernel(int P, const float* __restrict__ means3D, const in
         const float m_w = 1.0f / (m_hom_w + 0.0000001f);
         const float mul1 = (proj[0] * mx + proj[4] * my + proj[8] * mz + proj[12]) * m_w * m_w;
         const float mul2 = (proj[1] * mx + proj[5] * my + proj[9] * mz + proj[13]) * m_w * m_w;
-        const float gx2 = dL_dmean2D[3 * idx + 0], gy2 = dL_dmean2D[3 * idx + 1];
+        const float gx2 = a2.z, gy2 = a2.w;
         dmx += (proj[0] * m_w - proj[3] * mul1) * gx2 + (proj[1] * m_w - proj[3] * mul2) * gy2;
         dmy += (proj[4] * m_w - proj[7] * mul1) * gx2 + (proj[5] * m_w - proj[7] * mul2) * gy2;
         dmz += (proj[8] * m_w - proj[11] * mul1) * gx2 + (proj[9] * m_w - proj[11] * mul2) * gy2;
@@ -180,15 +197,16 @@ void gh_launch_preprocess_backward(int P, const float* means3D, const int* radii
                                    const float* cov3D_precomp, const float* conic_precomp,
                                    const float* viewmatrix, const float* projmatrix,
                                    int W, int H, float tan_fovx, float tan_fovy,
-                                   const float* dL_dmean2D, const float* dL_dconic,
+                                   const float* acc16, float* dL_dmean2D, float* dL_dconic,
+                                   float* dL_dopacity, float* dL_dcolor,
                                    float* dL_dmean3D, float* dL_dcov3D, float* dL_dscale, float* dL_drot,
                                    cudaStream_t stream)
 {
-    if (conic_precomp != nullptr) return;   // reference: geometry backward is a no-op in this mode
+    if (conic_precomp != nullptr) return;   // reference: geometry backward is a no-op in this mode (caller unpacks)
     const float focal_y = H / (2.0f * tan_fovy);
     const float focal_x = W / (2.0f * tan_fovx);
     gh_preprocess_backward_kernel<<<(P + 255) / 256, 256, 0, stream>>>(
         P, means3D, radii, scales, scale_modifier, rotations, cov3D_precomp, viewmatrix, projmatrix,
-        focal_x, focal_y, tan_fovx, tan_fovy, dL_dmean2D, dL_dconic,
+        focal_x, focal_y, tan_fovx, tan_fovy, acc16, dL_dmean2D, dL_dconic, dL_dopacity, dL_dcolor,
         dL_dmean3D, dL_dcov3D, dL_dscale, dL_drot);
 }
