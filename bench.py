@@ -340,8 +340,15 @@ def main():
             gbs = stage_bytes[name] / (avg * 1e-3) / 1e9 if avg > 0 else 0.0
             stages[name] = {"ms": avg, "alg_bytes": int(stage_bytes[name]), "gbs": gbs, "frac": gbs / peak}
         dom = max(stages, key=lambda k: stages[k]["ms"])
+        traffic = None
+        try:     # DRAM bytes per launch of that kernel from the committed ncu --set full capture
+            import glob
+            tf = sorted(glob.glob(os.path.join(ROOT, "profiles", "r*_traffic.json")))[-1]
+            traffic = json.load(open(tf)).get(dom) if args.mode == "native" else None
+        except Exception:
+            traffic = None
         roofline = {"bound": "hbm", "kernel": dom, "achieved": stages[dom]["gbs"], "peak": peak, "unit": "GB/s",
-                    "frac": stages[dom]["frac"], "traffic": None, "peak_source": peak_src,
+                    "frac": stages[dom]["frac"], "traffic": traffic, "peak_source": peak_src,
                     "ms": stages[dom]["ms"], "alg_bytes": stages[dom]["alg_bytes"],
                     "timing": f"CUDA events around each stage on the launching stream, {nrf} steps after the timed region"}
     if use_dist:

@@ -120,9 +120,11 @@ def rasterize_gaussians(
     return R, out_color, radii, geomBuffer, binningBuffer, imgBuffer
 
 
-def alloc_grad_arena(P: int, device: torch.device):
-    """One zero-filled flat float32 buffer holding all per-Gaussian gradients + named (P, n) views."""
-    flat = torch.zeros(P * GRAD_FLOATS_PER_GAUSSIAN, dtype=torch.float32, device=device)
+def alloc_grad_arena(P: int, device: torch.device, zero: bool = True):
+    """One flat float32 buffer holding all per-Gaussian gradients + named (P, n) views.
+    `zero=False` skips the fill: gh_backward writes every element itself."""
+    alloc = torch.zeros if zero else torch.empty
+    flat = alloc(P * GRAD_FLOATS_PER_GAUSSIAN, dtype=torch.float32, device=device)
     views, off = {}, 0
     for name, n in _GRAD_LAYOUT:
         views[name] = flat[off:off + P * n].view(P, n)
@@ -143,7 +145,7 @@ def rasterize_gaussians_backward_arena(
     P = int(means3D.size(0))
     H, W = int(dL_dout_color.size(1)), int(dL_dout_color.size(2))
     M = int(sh.size(1)) if sh.numel() != 0 else 0
-    flat, g = alloc_grad_arena(P, device)
+    flat, g = alloc_grad_arena(P, device, zero=False)     # gh_backward writes every element
     dL_dsh = torch.zeros((P, M, 3), dtype=torch.float32, device=device)
     if P != 0:
         with torch.cuda.device(device):

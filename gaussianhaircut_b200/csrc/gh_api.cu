@@ -258,6 +258,16 @@ int gh_backward(
     GhImgWS img = GhImgWS::carve(img_buffer, (size_t)width * height, (size_t)T);
     GhBinWS bin = GhBinWS::carve(binning_buffer, (size_t)R);
 
+    if (R == 0) {
+        // nothing was rendered: every gradient is zero (P * floats-per-row each)
+        struct { float* p; size_t n; } z[] = {{dL_dmean2D, 3}, {dL_dconic, 4}, {dL_dopacity, 1}, {dL_dcolor, GH_NUM_CHANNELS},
+                                              {dL_dmean3D, 3}, {dL_dcov3D, 6}, {dL_dscale, 3}, {dL_drot, 4}};
+        for (auto& b : z)
+            if (b.p) {
+                cudaError_t e = cudaMemsetAsync(b.p, 0, (size_t)P * b.n * sizeof(float), stream);
+                if (e != cudaSuccess) return gh_check_cuda(e, "memset(gradients)");
+            }
+    }
     if (R > 0) {
         GhStageTimer t(GH_ST_BLEND_BWD, stream);
         cudaError_t e = cudaMemsetAsync(geom.acc16, 0, (size_t)P * 64, stream);
@@ -265,7 +275,8 @@ int gh_backward(
         gh_launch_blend_backward(width, height, gx, gy, geom, img, bin, colors_precomp, background, dL_dpix, stream);
         g_launches += 1;
         if (conic_precomp != nullptr) {   // otherwise the geometry backward unpacks the records itself
-            gh_launch_unpack_grads(P, geom, dL_dmean2D, dL_dconic, dL_dopacity, dL_dcolor, stream);
+            gh_launch_unpack_grads(P, geom, dL_dmean2D, dL_dconic, dL_dopacity, dL_dcolor,
+                                   dL_dmean3D, dL_dcov3D, dL_dscale, dL_drot, stream);
             g_launches += 1;
         }
     }

@@ -566,7 +566,9 @@ gh_blend_backward_kernel(const uint2* __restrict__ ranges, const uint64_t* __res
 // dL_dmean2D (P,3) [z never written by the reference: 0], dL_dconic (P,2,2) [.z unused: 0], dL_dopacity (P,1)
 __global__ void __launch_bounds__(256)
 gh_unpack_grads_kernel(int P, const float* __restrict__ acc16, float* __restrict__ dL_dmean2D,
-                       float* __restrict__ dL_dconic, float* __restrict__ dL_dopacity, float* __restrict__ dL_dcolor)
+                       float* __restrict__ dL_dconic, float* __restrict__ dL_dopacity, float* __restrict__ dL_dcolor,
+                       float* __restrict__ dL_dmean3D, float* __restrict__ dL_dcov3D,
+                       float* __restrict__ dL_dscale, float* __restrict__ dL_drot)
 {
     const int idx = blockIdx.x * blockDim.x + threadIdx.x;
     if (idx >= P) return;
@@ -579,6 +581,14 @@ gh_unpack_grads_kernel(int P, const float* __restrict__ acc16, float* __restrict
     dL_dmean2D[3 * idx + 0] = a2.z; dL_dmean2D[3 * idx + 1] = a2.w; dL_dmean2D[3 * idx + 2] = 0.f;
     reinterpret_cast<float4*>(dL_dconic)[idx] = make_float4(a3.x, a3.y, 0.f, a3.z);
     dL_dopacity[idx] = a3.w;
+    // conic supplied by the caller: nothing flows through the geometry (reference backward.cu:371,398,588)
+    if (dL_dmean3D) { dL_dmean3D[3 * idx + 0] = 0.f; dL_dmean3D[3 * idx + 1] = 0.f; dL_dmean3D[3 * idx + 2] = 0.f; }
+    if (dL_dcov3D) {
+#pragma unroll
+        for (int k = 0; k < 6; k++) dL_dcov3D[6 * idx + k] = 0.f;
+    }
+    if (dL_dscale) { dL_dscale[3 * idx + 0] = 0.f; dL_dscale[3 * idx + 1] = 0.f; dL_dscale[3 * idx + 2] = 0.f; }
+    if (dL_drot) reinterpret_cast<float4*>(dL_drot)[idx] = make_float4(0.f, 0.f, 0.f, 0.f);
 }
 
 }  // namespace
@@ -604,8 +614,10 @@ void gh_launch_blend_backward(int W, int H, int gx, int gy, GhGeomWS geom, GhImg
 }
 
 void gh_launch_unpack_grads(int P, GhGeomWS geom, float* dL_dmean2D, float* dL_dconic, float* dL_dopacity,
-                            float* dL_dcolor, cudaStream_t stream)
+                            float* dL_dcolor, float* dL_dmean3D, float* dL_dcov3D, float* dL_dscale, float* dL_drot,
+                            cudaStream_t stream)
 {
     gh_unpack_grads_kernel<<<(P + 255) / 256, 256, 0, stream>>>(P, geom.acc16, dL_dmean2D, dL_dconic,
-                                                                dL_dopacity, dL_dcolor);
+                                                                dL_dopacity, dL_dcolor, dL_dmean3D, dL_dcov3D,
+                                                                dL_dscale, dL_drot);
 }

@@ -32,8 +32,10 @@ void gh_launch_blend_backward(int W, int H, int gx, int gy, GhGeomWS geom, GhImg
                               cudaStream_t stream);
 
 // geom.acc16 -> dL_dmean2D (P,3), dL_dconic (P,4), dL_dopacity (P), dL_dcolor (P,10); writes every row
+// (also zero-fills the geometry gradients that are non-null: used when the conic was supplied)
 void gh_launch_unpack_grads(int P, GhGeomWS geom, float* dL_dmean2D, float* dL_dconic, float* dL_dopacity,
-                            float* dL_dcolor, cudaStream_t stream);
+                            float* dL_dcolor, float* dL_dmean3D, float* dL_dcov3D, float* dL_dscale, float* dL_drot,
+                            cudaStream_t stream);
 
 void gh_launch_preprocess_backward(int P, const float* means3D, const int* radii,
                                    const float* scales, float scale_modifier, const float* rotations,

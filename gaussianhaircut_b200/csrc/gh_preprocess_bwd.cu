@@ -41,7 +41,16 @@ gh_preprocess_backward_kernel(int P, const float* __restrict__ means3D, const in
         reinterpret_cast<float4*>(dL_dconic)[idx] = make_float4(a3.x, a3.y, 0.f, a3.z);
         dL_dopacity[idx] = a3.w;
     }
-    if (!(radii[idx] > 0)) return;
+    if (!(radii[idx] > 0)) {
+        // not rendered: all geometry gradients are zero (every output row is written, so the caller
+        // does not have to zero-fill the buffers)
+        dL_dmean3D[3 * idx + 0] = 0.f; dL_dmean3D[3 * idx + 1] = 0.f; dL_dmean3D[3 * idx + 2] = 0.f;
+#pragma unroll
+        for (int k = 0; k < 6; k++) dL_dcov3D[6 * idx + k] = 0.f;
+        if (dL_dscale) { dL_dscale[3 * idx + 0] = 0.f; dL_dscale[3 * idx + 1] = 0.f; dL_dscale[3 * idx + 2] = 0.f; }
+        if (dL_drot) reinterpret_cast<float4*>(dL_drot)[idx] = make_float4(0.f, 0.f, 0.f, 0.f);
+        return;
+    }
 
     const float mx = means3D[3 * idx + 0], my = means3D[3 * idx + 1], mz = means3D[3 * idx + 2];
 
@@ -148,7 +157,10 @@ gh_preprocess_backward_kernel(int P, const float* __restrict__ means3D, const in
     dL_dmean3D[3 * idx + 2] = dmz;
 
     // ---- backward of computeCov3D (backward.cu:278-341) --------------------------------------
-    if (from_scale_rot && scales != nullptr) {
+    if (!(from_scale_rot && scales != nullptr)) {
+        if (dL_dscale) { dL_dscale[3 * idx + 0] = 0.f; dL_dscale[3 * idx + 1] = 0.f; dL_dscale[3 * idx + 2] = 0.f; }
+        if (dL_drot) reinterpret_cast<float4*>(dL_drot)[idx] = make_float4(0.f, 0.f, 0.f, 0.f);
+    } else {
         const float r = q.x, x = q.y, y = q.z, z = q.w;
         // R[c][r] as the glm ctor fills it (columns)
         const float R00 = 1.f - 2.f * (y * y + z * z), R01 = 2.f * (x * y - r * z), R02 = 2.f * (x * z + r * y);

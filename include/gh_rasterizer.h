@@ -124,8 +124,9 @@ int gh_forward_render(
     int debug, gh_stream_t stream);
 
 /*
- * Rasterizer::backward (rasterizer.h:57-87).  All nine gradient buffers must be zero-filled by the
- * caller (the reference's binding does torch::zeros, rasterize_points.cu:160-168); shapes as there:
+ * Rasterizer::backward (rasterizer.h:57-87).  Every element of every non-NULL gradient buffer is
+ * written (zeros where nothing flows), so the caller need NOT zero-fill them (the reference's binding
+ * does torch::zeros, rasterize_points.cu:160-168).  dL_dsh is never touched.  Shapes as there:
  * dL_dmean2D (P,3) [NDC units, z unused], dL_dconic (P,2,2) [.x .y .w used, .y = half the
  * off-diagonal derivative], dL_dopacity (P,1), dL_dcolor (P,C), dL_dmean3D (P,3), dL_dcov3D (P,6),
  * dL_dsh (P,M,3) [never written: SH path unreachable with C = 10], dL_dscale (P,3), dL_drot (P,4).
