@@ -64,6 +64,7 @@ SIGNATURES = {
         _p, _p, _p, _p, _p,                  # dL_dmean3D dL_dcov3D dL_dsh dL_dscale dL_drot
         _i, _p]),                            # debug stream
     "gh_mark_visible": (_i, [_i, _p, _p, _p, _p, _p]),
+    "gh_adam_step": (_i, [_i, _p, _p, _p, _p, _p, _p, _f, _f, _f, _i, _p, _p, _p]),
     "gh_debug_export": (_i, [_i, _i, _i, _ll, _p, _p, _p, _p, _p, _p, _p, _p, _p, _p, _p, _p]),
 }
 

@@ -168,6 +168,23 @@ int gh_debug_export(
     float* depths, float* means2D, float* conic_opacity,
     gh_stream_t stream);
 
+/*
+ * "Next" row: fused multi-group Adam step with torch.optim.Adam's arithmetic
+ * (reference: src/scene/gaussian_model.py:431-448, stepped at src/train_gaussians.py:174-181).
+ * params/grads/exp_avg/exp_avg_sq are HOST arrays of n_groups (<= GH_ADAM_MAX_GROUPS) device pointers,
+ * sizes[k] the element count and lrs[k] the learning rate of group k; `step` is 1-based and used when
+ * step_state is NULL; otherwise step_state is a device int[2] {steps taken, scratch} owned by the caller
+ * (zero-initialised) and the step count lives on the device (advanced only by steps that were not skipped).
+ * nan_flag (device uint, may be NULL): when given, the step is skipped on the device if any gradient
+ * holds a NaN and the flag is left non-zero (the reference's NaN guard without its host syncs).
+ */
+#define GH_ADAM_MAX_GROUPS 8
+int gh_adam_step(int n_groups, float* const* params, const float* const* grads,
+                 float* const* exp_avg, float* const* exp_avg_sq,
+                 const unsigned long long* sizes, const float* lrs,
+                 float beta1, float beta2, float eps, int step, int* step_state,
+                 unsigned int* nan_flag, gh_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -235,3 +235,32 @@ def test_api_errors(cuda_device):
     bad = kw["means3D"].clone(); bad[0] = 3.0 * s["campos"]
     with pytest.raises(RuntimeError, match="filtered although prefiltered"):
         rast2(**{**kw, "means3D": bad})
+
+
+def test_fused_adam_matches_torch(cuda_device):
+    """'Next' row 2: gh_adam_step == torch.optim.Adam(eps=1e-15) with per-group lr, incl. the NaN guard."""
+    from gaussianhaircut_b200.optim import FusedAdam
+    torch.manual_seed(0)
+    shapes = [(5000, 3), (5000, 1, 3), (5000, 15, 3), (5000, 1), (5000, 1), (5000, 3), (5000, 4)]
+    lrs = [1.6e-4, 2.5e-3, 2.5e-3 / 20, 0.05, 0.0025, 0.005, 0.001]
+    p_ref = [torch.randn(s, device=cuda_device).requires_grad_(True) for s in shapes]
+    p_mine = [p.detach().clone().requires_grad_(True) for p in p_ref]
+    opt_ref = torch.optim.Adam([{"params": [p], "lr": lr} for p, lr in zip(p_ref, lrs)], lr=0.0, eps=1e-15)
+    opt_mine = FusedAdam([{"params": [p], "lr": lr} for p, lr in zip(p_mine, lrs)], eps=1e-15)
+    for it in range(6):
+        grads = [torch.randn_like(p) * (10.0 ** (it - 3)) for p in p_ref]
+        poisoned = (it == 3)
+        if poisoned:
+            grads[2][7, 3, 1] = float("nan")
+        for p, q, g in zip(p_ref, p_mine, grads):
+            p.grad = g.clone(); q.grad = g.clone()
+        # the reference's guard (train_gaussians.py:174-181): drop all grads if any has a NaN, then step
+        if any(bool(p.grad.isnan().any()) for p in p_ref):
+            opt_ref.zero_grad(set_to_none=True)
+        opt_ref.step()
+        opt_mine.step()
+        torch.cuda.synchronize()
+        assert bool(opt_mine.nan_flag.item() != 0) == poisoned
+        for p, q in zip(p_ref, p_mine):
+            assert rel_err(q.detach(), p.detach()) <= 1e-6, f"step {it}"
+    assert int(opt_mine.step_state[0]) == 5        # the poisoned step was skipped, like torch's state['step']
