@@ -217,6 +217,7 @@ def main():
             if use_dist:
                 dist.all_reduce(flat, op=dist.ReduceOp.SUM)     # one collective per step over the whole arena
             last["grads"] = flat
+            last["views"] = grads
         else:
             last["grads"] = mod.rasterize_gaussians_backward(*bw)
         last["R"] = R
@@ -259,6 +260,53 @@ def main():
     value = (args.steps * P * n_eff) / (ms_total * 1e-3)
     R_mean = float(last["R"])
     log(f"[bench] {args.impl}: {ms_per_step:.3f} ms/step  -> {value / 1e6:.1f} M Gaussians/s  (R={last['R']})")
+
+    # ---------------------------------------------------------------- second figure: + Adam step (BASELINE config 3)
+    with_adam = None
+    if args.mode == "native" and not use_dist:
+        pnames = ("means3D", "scales", "rotations", "colors_precomp", "opacities")
+        gnames = ("means3D", "scales", "rotations", "colors", "opacity")
+        # the op's inputs are activated values (not the trainer's log-/logit-space parameters): keep the
+        # updates negligible so that the workload (R, splat sizes) stays the one being measured
+        lrs = (1e-9, 1e-10, 1e-9, 1e-9, 1e-9)
+        kw0 = packed[0][1]
+        plist = [kw0[n] for n in pnames]
+        if args.impl == "mine":
+            from gaussianhaircut_b200.optim import FusedAdam
+            opt = FusedAdam([{"params": [p], "lr": lr} for p, lr in zip(plist, lrs)], eps=1e-15)
+
+            def adam_step(i):
+                step(0)
+                opt.step(grads=[last["views"][g].reshape(p.shape) for g, p in zip(gnames, plist)])
+        else:
+            for p in plist:
+                p.requires_grad_(True)
+            opt = torch.optim.Adam([{"params": [p], "lr": lr} for p, lr in zip(plist, lrs)], lr=0.0, eps=1e-15)
+            gidx = {"means3D": 3, "scales": 7, "rotations": 8, "colors": 1, "opacity": 2}   # positions in the 9-tuple
+
+            def adam_step(i):
+                step(0)
+                g9 = last["grads"]
+                for gname, p in zip(gnames, plist):
+                    p.grad = g9[gidx[gname]].reshape(p.shape)
+                # the reference trainer's NaN guard: one blocking .isnan().any() per parameter (train_gaussians.py:175-178)
+                for p in plist:
+                    if p.grad is not None and p.grad.isnan().any():
+                        opt.zero_grad(set_to_none=True)
+                opt.step()
+                opt.zero_grad(set_to_none=True)
+        with torch.no_grad():
+            saved = [p.detach().clone() for p in plist]
+            for i in range(3):
+                adam_step(i)
+            ms_adam = timed(args.steps, adam_step)
+            for p, q in zip(plist, saved):
+                p.copy_(q)                                   # restore the scene for the following sections
+        with_adam = {"ms_per_step": ms_adam / args.steps, "value": args.steps * P / (ms_adam * 1e-3), "unit": UNIT,
+                     "optimizer": "gh_adam_step (fused, device-side NaN guard)" if args.impl == "mine"
+                                  else "torch.optim.Adam + per-parameter isnan().any() host syncs (reference trainer)",
+                     "parameters": list(pnames)}
+        log(f"[bench] +Adam: {with_adam['ms_per_step']:.3f} ms/step -> {with_adam['value'] / 1e6:.1f} M Gaussians/s")
 
     # ---------------------------------------------------------------- end to end through the public API
     e2e = None
@@ -394,6 +442,7 @@ def main():
             "path_roofline": {"alg_bytes": int(path_bytes), "achieved": path_gbs, "peak": peak, "unit": "GB/s",
                               "frac": path_gbs / peak, "formula": "400P+52R+96WH+24T (344P if conic supplied)"},
             "stages": stages,
+            "with_adam": with_adam,
             "cpu_baseline": cpu_baseline,
         }
         if args.impl == "reference":
