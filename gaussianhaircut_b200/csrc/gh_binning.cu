@@ -175,14 +175,19 @@ void gh_launch_emit(int P, const int* radii, GhGeomWS geom, GhImgWS img, GhBinWS
 int gh_launch_tile_sort(int T, unsigned int max_tile_len, GhImgWS img, GhBinWS bin, cudaStream_t stream)
 {
     // tiles with at most GH_INKERNEL_SORT_MAX instances are sorted by the forward blend CTA itself
-    // (gh_blend.cu); only longer lists need this kernel
+    // (gh_blend.cu); only longer lists need these kernels
     constexpr uint32_t SMALL = GH_INKERNEL_SORT_MAX;
-    constexpr uint32_t LARGE = 24576;    // 192 KB of keys, 1024 threads
+    constexpr uint32_t MID = 8192;       //  64 KB of keys, 1024 threads, 2-3 CTAs per SM
+    constexpr uint32_t LARGE = 24576;    // 192 KB of keys, 1024 threads, 1 CTA per SM; beyond: in place in global
+    int launches = 0;
     if (max_tile_len > SMALL) {
-        cudaFuncSetAttribute(gh_tile_sort_kernel<1024>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                             (int)(LARGE * 8));
-        gh_tile_sort_kernel<1024><<<T, 1024, LARGE * 8, stream>>>(img.ranges, bin.inst, SMALL, 0xffffffffu, LARGE);
-        return 1;
+        cudaFuncSetAttribute(gh_tile_sort_kernel<1024>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(LARGE * 8));
+        gh_tile_sort_kernel<1024><<<T, 1024, MID * 8, stream>>>(img.ranges, bin.inst, SMALL, MID, MID);
+        launches++;
     }
-    return 0;
+    if (max_tile_len > MID) {
+        gh_tile_sort_kernel<1024><<<T, 1024, LARGE * 8, stream>>>(img.ranges, bin.inst, MID, 0xffffffffu, LARGE);
+        launches++;
+    }
+    return launches;
 }
