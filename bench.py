@@ -346,19 +346,26 @@ def main():
                 sl["campos"].copy_(hv["campos"], non_blocking=True)
                 sl["ready"].record(copy_stream)
 
-        e2e_state = {"next": 0}
+        e2e_state = {"next": 0, "overlap": True}
 
         def e2e_step(i):
-            if e2e_state["next"] <= i:                            # first step of a timed run: nothing prefetched yet
-                prefetch(i)
-                e2e_state["next"] = i + 1
             j = i % len(views)
             s = views[j]["settings"]
             sl = slots[i % 2]
             cur = torch.cuda.current_stream(device)
-            cur.wait_event(sl["ready"])
-            prefetch(i + 1)                                       # overlaps with this step's compute
-            e2e_state["next"] = i + 2
+            if e2e_state["overlap"]:
+                if e2e_state["next"] <= i:                        # first step of a timed run: nothing prefetched yet
+                    prefetch(i)
+                    e2e_state["next"] = i + 1
+                cur.wait_event(sl["ready"])
+                prefetch(i + 1)                                   # overlaps with this step's compute
+                e2e_state["next"] = i + 2
+            else:                                                 # serial loader: copy, then compute, on one stream
+                hv = host_views[j]
+                sl["Wt"].copy_(Wt_host, non_blocking=True)
+                sl["view"].copy_(hv["view"], non_blocking=True)
+                sl["proj"].copy_(hv["proj"], non_blocking=True)
+                sl["campos"].copy_(hv["campos"], non_blocking=True)
             settings = mod.GaussianRasterizationSettings(
                 image_height=s["image_height"], image_width=s["image_width"], tanfovx=s["tanfovx"],
                 tanfovy=s["tanfovy"], bg=s["bg"], scale_modifier=1.0, viewmatrix=sl["view"], projmatrix=sl["proj"],
@@ -383,13 +390,28 @@ def main():
         for i in range(len(views) + max(3, args.warmup)):
             e2e_step(i)
         e2e_steps = max(2 * len(views), args.steps // 2)
-        torch.cuda.synchronize()
-        e2e_state["next"] = 0
-        ms_e2e = timed(e2e_steps, e2e_step)
-        copy_stream.synchronize()
+        # both loader styles are measured and the faster one is reported for this arm (the reference's
+        # synchronous cudaMemcpy/cudaMemset inside its forward serialise against a concurrent H2D stream)
+        results = {}
+        for overlap in (True, False):
+            e2e_state["overlap"] = overlap
+            torch.cuda.synchronize(); copy_stream.synchronize()
+            e2e_state["next"] = 0
+            for sl in slots:
+                sl["free"].record(torch.cuda.current_stream(device))
+            for i in range(3):
+                e2e_step(i)
+            torch.cuda.synchronize(); copy_stream.synchronize()
+            e2e_state["next"] = 0
+            results[overlap] = timed(e2e_steps, e2e_step)
+            copy_stream.synchronize()
+        best_overlap = min(results, key=results.get)
+        ms_e2e = results[best_overlap]
         e2e_value = (e2e_steps * P * n_eff) / (ms_e2e * 1e-3)
         e2e = {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": 4,
                "ms_per_step": ms_e2e / e2e_steps, "steps": e2e_steps,
+               "loader": "prefetch on a copy stream" if best_overlap else "serial copy on the compute stream",
+               "ms_per_step_prefetch": results[True] / e2e_steps, "ms_per_step_serial": results[False] / e2e_steps,
                "api": "GaussianRasterizer(...)(**tensors) + autograd backward; every step copies its camera + (10,H,W) "
                       "supervision tensor from pinned host memory (double-buffered on a copy stream, overlapping the "
                       "previous step's compute) and reads loss.item() back"}
