@@ -207,7 +207,7 @@ int gh_forward_render(
         GH_STAGE(stream, debug, "emit");
         {
             GhStageTimer t(GH_ST_TILE_SORT, stream);
-            g_launches += gh_launch_tile_sort(T, (unsigned int)max_tile_len, img, bin, stream);
+            g_launches += gh_launch_tile_sort(T, (unsigned int)max_tile_len, (long long)num_rendered, img, bin, stream);
         }
         GH_STAGE(stream, debug, "tile sort");
     }

@@ -134,6 +134,101 @@ gh_emit_kernel(int P, const int* __restrict__ radii, const GhGeo* __restrict__ g
 }
 
 // ---------------------------------------------------------------- per-tile sort (network in gh_common.cuh)
+// Long lists (more than GH_INKERNEL_SORT_MAX records in a tile; the forward CTA sorts shorter ones
+// itself) are sorted in linear time by two kernels:
+//   split: one 256-thread CTA per long tile finds the depth range of the list, splits it (MSD, order
+//          preserving) into segments of ~768 records by linearly quantised depth, scatters the records
+//          into the scratch buffer segment by segment and appends (start, length) descriptors;
+//   sort:  one CTA per segment sorts it in shared memory (gh_bucket_sort_tile) into its final place.
+// A segment that still exceeds the shared buffer (heavily clustered depths) uses the in-place network.
+#define GH_LONG_MAX_SUPER 1024
+__global__ void __launch_bounds__(256)
+gh_tile_split_long_kernel(const uint2* __restrict__ ranges, const uint64_t* __restrict__ inst, uint64_t* __restrict__ tmp,
+                          uint2* __restrict__ seg, GhCtrl* ctrl, uint32_t lo)
+{
+    __shared__ uint32_t s_cnt[GH_LONG_MAX_SUPER];
+    __shared__ uint32_t s_red[16];
+    __shared__ uint32_t s_segbase;
+    const uint2 rg = ranges[blockIdx.x];
+    const uint32_t n = rg.y - rg.x;
+    if (n <= lo) return;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const uint64_t* src = inst + rg.x;
+    uint64_t* dst = tmp + rg.x;
+    uint32_t dmin = 0xffffffffu, dmax = 0u;
+    for (uint32_t i = tid; i < n; i += 256) { const uint32_t d = (uint32_t)(src[i] >> 32); dmin = min(dmin, d); dmax = max(dmax, d); }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        dmin = min(dmin, __shfl_xor_sync(0xffffffffu, dmin, o));
+        dmax = max(dmax, __shfl_xor_sync(0xffffffffu, dmax, o));
+    }
+    if (lane == 0) { s_red[warp] = dmin; s_red[8 + warp] = dmax; }
+    const uint32_t nsuper = min((uint32_t)GH_LONG_MAX_SUPER, (n + 767u) / 768u);
+    for (uint32_t i = tid; i < nsuper; i += 256) s_cnt[i] = 0u;
+    if (tid == 0) s_segbase = atomicAdd(&ctrl->nseg, nsuper);
+    __syncthreads();
+#pragma unroll
+    for (int w = 0; w < 8; w++) { dmin = min(dmin, s_red[w]); dmax = max(dmax, s_red[8 + w]); }
+    const float inv = (float)nsuper / ((float)(dmax - dmin) + 1.0f);
+    for (uint32_t i = tid; i < n; i += 256) {
+        const uint32_t d = (uint32_t)(src[i] >> 32);
+        atomicAdd(&s_cnt[min(nsuper - 1u, (uint32_t)((float)(d - dmin) * inv))], 1u);
+    }
+    __syncthreads();
+    {   // exclusive scan of nsuper counts: thread t owns 4 consecutive counters
+        uint32_t c[4], sum = 0;
+#pragma unroll
+        for (int k = 0; k < 4; k++) { const uint32_t j = tid * 4 + k; c[k] = j < nsuper ? s_cnt[j] : 0u; sum += c[k]; }
+        uint32_t v = sum;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) { const uint32_t nb = __shfl_up_sync(0xffffffffu, v, o); if (lane >= o) v += nb; }
+        __syncthreads();
+        if (lane == 31) s_red[warp] = v;
+        __syncthreads();
+        uint32_t run = v - sum;
+#pragma unroll
+        for (int w = 0; w < 8; w++) run += (w < warp) ? s_red[w] : 0u;
+#pragma unroll
+        for (int k = 0; k < 4; k++) {
+            const uint32_t j = tid * 4 + k;
+            if (j < nsuper) {
+                s_cnt[j] = run;
+                seg[s_segbase + j] = make_uint2(rg.x + run, c[k]);
+            }
+            run += c[k];
+        }
+    }
+    __syncthreads();
+    for (uint32_t i = tid; i < n; i += 256) {
+        const uint64_t key = src[i];
+        const uint32_t d = (uint32_t)(key >> 32);
+        dst[atomicAdd(&s_cnt[min(nsuper - 1u, (uint32_t)((float)(d - dmin) * inv))], 1u)] = key;
+    }
+}
+
+__global__ void __launch_bounds__(256)
+gh_segment_sort_kernel(const uint2* __restrict__ seg, const GhCtrl* __restrict__ ctrl, uint64_t* inst, uint64_t* tmp)
+{
+    __shared__ __align__(16) uint64_t sA[GH_INKERNEL_SORT_MAX];
+    __shared__ __align__(16) uint64_t sB[GH_INKERNEL_SORT_MAX];
+    __shared__ uint32_t s_small[3 * 256];
+    if (blockIdx.x >= ctrl->nseg) return;
+    const uint2 sg = seg[blockIdx.x];
+    const uint32_t b0 = sg.x, m = sg.y;
+    if (m == 0) return;
+    const int tid = threadIdx.x;
+    if (m <= GH_INKERNEL_SORT_MAX) {
+        for (uint32_t i = tid; i < m; i += 256) sA[i] = tmp[b0 + i];
+        __syncthreads();
+        if (m <= 64) gh_bitonic_sort(sA, m, tid, 256);
+        else gh_bucket_sort_tile(sA, sB, s_small, (int)m, tid);
+        for (uint32_t i = tid; i < m; i += 256) inst[b0 + i] = sA[i];
+    } else {
+        gh_bitonic_sort(tmp + b0, m, tid, 256);
+        for (uint32_t i = tid; i < m; i += 256) inst[b0 + i] = tmp[b0 + i];
+    }
+}
+
 // SMEM_KEYS: capacity of the shared staging buffer; handles tiles with lo < n <= hi.
 // Tiles longer than the buffer are sorted in place in global memory by the same network.
 template <int NT>
@@ -172,22 +267,13 @@ void gh_launch_emit(int P, const int* radii, GhGeomWS geom, GhImgWS img, GhBinWS
                                                         img.tile_cursor, bin.inst, gx, gy);
 }
 
-int gh_launch_tile_sort(int T, unsigned int max_tile_len, GhImgWS img, GhBinWS bin, cudaStream_t stream)
+int gh_launch_tile_sort(int T, unsigned int max_tile_len, long long R, GhImgWS img, GhBinWS bin, cudaStream_t stream)
 {
     // tiles with at most GH_INKERNEL_SORT_MAX instances are sorted by the forward blend CTA itself
     // (gh_blend.cu); only longer lists need these kernels
-    constexpr uint32_t SMALL = GH_INKERNEL_SORT_MAX;
-    constexpr uint32_t MID = 8192;       //  64 KB of keys, 1024 threads, 2-3 CTAs per SM
-    constexpr uint32_t LARGE = 24576;    // 192 KB of keys, 1024 threads, 1 CTA per SM; beyond: in place in global
-    int launches = 0;
-    if (max_tile_len > SMALL) {
-        cudaFuncSetAttribute(gh_tile_sort_kernel<1024>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(LARGE * 8));
-        gh_tile_sort_kernel<1024><<<T, 1024, MID * 8, stream>>>(img.ranges, bin.inst, SMALL, MID, MID);
-        launches++;
-    }
-    if (max_tile_len > MID) {
-        gh_tile_sort_kernel<1024><<<T, 1024, LARGE * 8, stream>>>(img.ranges, bin.inst, MID, 0xffffffffu, LARGE);
-        launches++;
-    }
-    return launches;
+    if (max_tile_len <= GH_INKERNEL_SORT_MAX) return 0;
+    gh_tile_split_long_kernel<<<T, 256, 0, stream>>>(img.ranges, bin.inst, bin.tmp, bin.seg, img.ctrl, GH_INKERNEL_SORT_MAX);
+    const unsigned int nseg_max = (unsigned int)GhBinWS::max_segments((size_t)R);   // >= sum over long tiles of ceil(n/768)
+    gh_segment_sort_kernel<<<nseg_max, 256, 0, stream>>>(bin.seg, img.ctrl, bin.inst, bin.tmp);
+    return 2;
 }

@@ -262,10 +262,12 @@ gh_blend_forward_kernel(const uint2* __restrict__ ranges, uint64_t* inst,
     // backward pass.  Longer lists were sorted by gh_tile_sort_kernel before this launch.
     if (n >= 2 && n <= (int)GH_INKERNEL_SORT_MAX) {
         uint64_t* skeys = reinterpret_cast<uint64_t*>(&st.g0[0][0]);     // g0 + g1 = 16 KB contiguous
+        uint64_t* spong = reinterpret_cast<uint64_t*>(&st.feat[0][0]);   // next 16 KB (feat is 20 KB)
         uint64_t* gl = inst + rg.x;
         for (int i = tid; i < n; i += 256) skeys[i] = gl[i];
         __syncthreads();
-        gh_bitonic_sort(skeys, (uint32_t)n, tid, 256);
+        if (n <= 64) gh_bitonic_sort(skeys, (uint32_t)n, tid, 256);
+        else gh_bucket_sort_tile(skeys, spong, pixbits, n, tid);
         for (int i = tid; i < n; i += 256) gl[i] = skeys[i];
         __syncthreads();
     }

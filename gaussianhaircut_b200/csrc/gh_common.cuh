@@ -45,7 +45,7 @@ struct GhCtrl {
     unsigned int num_rendered;   // R = sum of per-tile instance counts
     unsigned int max_tile_len;   // longest per-tile list
     unsigned int err_flags;
-    unsigned int pad;
+    unsigned int nseg;           // segments produced by the long-list split (gh_binning.cu)
 };
 
 static __host__ __device__ __forceinline__ size_t gh_align_up(size_t v, size_t a) {
@@ -98,12 +98,18 @@ struct GhImgWS {
 
 struct GhBinWS {
     uint64_t* inst;   // [R]  (depth_bits << 32 | gaussian_idx), bucketed by tile, sorted within a tile
-    static __host__ __device__ size_t bytes(size_t R) { return gh_align_up(R * 8, 256) + 256; }
+    uint64_t* tmp;    // [R]  scratch of the long-list sort (MSD split target)
+    uint2* seg;       // [R/768 + R/2048 + 2] (start, length) of the split segments
+    static __host__ __device__ size_t max_segments(size_t R) { return R / 768 + R / 2048 + 2; }
+    static __host__ __device__ size_t bytes(size_t R) {
+        return 2 * gh_align_up(R * 8, 256) + gh_align_up(max_segments(R) * 8, 256) + 256;
+    }
     static __host__ __device__ GhBinWS carve(char* base, size_t R) {
         GhBinWS w;
         size_t off = gh_align_up((size_t)base, 256) - (size_t)base;
-        w.inst = (uint64_t*)(base + off);
-        (void)R;
+        w.inst = (uint64_t*)(base + off); off += gh_align_up(R * 8, 256);
+        w.tmp = (uint64_t*)(base + off); off += gh_align_up(R * 8, 256);
+        w.seg = (uint2*)(base + off);
         return w;
     }
 };
@@ -258,6 +264,86 @@ __device__ __forceinline__ void gh_bitonic_sort(KeyPtr keys, const uint32_t n, c
             __syncthreads();
         }
     }
+}
+
+// Sort up to 2048 records held in shared memory with a 256-thread CTA in linear time:
+// one MSD split of the records into 256 sub-buckets by linearly quantised depth (order preserving),
+// then every thread insertion-sorts one sub-bucket (a handful of records) on the full 64-bit
+// (depth bits, Gaussian index) key.  Sub-buckets that come out long (clustered depths) are sorted
+// by the whole CTA with the bitonic network.  A: records (in/out), B: scratch of the same size,
+// cnt: 3 x 256 words.
+__device__ __forceinline__ void gh_bucket_sort_tile(uint64_t* A, uint64_t* B, uint32_t* cnt, int n, int tid) {
+    __shared__ uint32_t s_red[16];
+    __shared__ uint32_t s_nbig;
+    const int lane = tid & 31, warp = tid >> 5;
+    uint32_t* off = cnt + 256;       // start of each sub-bucket
+    uint32_t* big = cnt + 512;       // list of sub-buckets too long for one thread
+    // depth range of the list
+    uint32_t dmin = 0xffffffffu, dmax = 0u;
+    for (int i = tid; i < n; i += 256) { const uint32_t d = (uint32_t)(A[i] >> 32); dmin = min(dmin, d); dmax = max(dmax, d); }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        dmin = min(dmin, __shfl_xor_sync(0xffffffffu, dmin, o));
+        dmax = max(dmax, __shfl_xor_sync(0xffffffffu, dmax, o));
+    }
+    if (lane == 0) { s_red[warp] = dmin; s_red[8 + warp] = dmax; }
+    cnt[tid] = 0u;
+    if (tid == 0) s_nbig = 0u;
+    __syncthreads();
+#pragma unroll
+    for (int w = 0; w < 8; w++) { dmin = min(dmin, s_red[w]); dmax = max(dmax, s_red[8 + w]); }
+    // monotone map depth bits -> sub-bucket 0..255
+    const float inv = 256.0f / ((float)(dmax - dmin) + 1.0f);
+    for (int i = tid; i < n; i += 256) {
+        const uint32_t d = (uint32_t)(A[i] >> 32);
+        const uint32_t b = min(255u, (uint32_t)((float)(d - dmin) * inv));
+        atomicAdd(&cnt[b], 1u);
+    }
+    __syncthreads();
+    {   // exclusive scan of the 256 counts (thread t owns sub-bucket t)
+        const uint32_t c = cnt[tid];
+        uint32_t v = c;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) { const uint32_t nb = __shfl_up_sync(0xffffffffu, v, o); if (lane >= o) v += nb; }
+        if (lane == 31) s_red[warp] = v;
+        __syncthreads();
+        uint32_t start = v - c;
+#pragma unroll
+        for (int w = 0; w < 8; w++) start += (w < warp) ? s_red[w] : 0u;
+        off[tid] = start;
+        __syncthreads();
+        cnt[tid] = start;            // becomes the scatter cursor
+    }
+    __syncthreads();
+    for (int i = tid; i < n; i += 256) {
+        const uint64_t key = A[i];
+        const uint32_t d = (uint32_t)(key >> 32);
+        const uint32_t b = min(255u, (uint32_t)((float)(d - dmin) * inv));
+        B[atomicAdd(&cnt[b], 1u)] = key;
+    }
+    __syncthreads();
+    {   // cnt[t] is now the END of sub-bucket t
+        const int b0 = (int)off[tid], b1 = (int)cnt[tid];
+        const int m = b1 - b0;
+        if (m > 24) {
+            big[atomicAdd(&s_nbig, 1u)] = (uint32_t)tid;
+        } else {
+            for (int i = b0 + 1; i < b1; i++) {
+                const uint64_t key = B[i];
+                int j = i - 1;
+                while (j >= b0 && B[j] > key) { B[j + 1] = B[j]; j--; }
+                B[j + 1] = key;
+            }
+        }
+    }
+    __syncthreads();
+    const uint32_t nbig = s_nbig;
+    for (uint32_t q = 0; q < nbig; q++) {
+        const uint32_t t = big[q];
+        gh_bitonic_sort(B + off[t], cnt[t] - off[t], tid, 256);   // ends with a barrier
+    }
+    for (int i = tid; i < n; i += 256) A[i] = B[i];
+    __syncthreads();
 }
 
 #endif  // __CUDACC__

@@ -20,7 +20,7 @@ void gh_launch_emit(int P, const int* radii, GhGeomWS geom, GhImgWS img, GhBinWS
 
 // sort every tile bucket by (depth bits, gaussian idx)
 // returns the number of kernels launched
-int gh_launch_tile_sort(int T, unsigned int max_tile_len, GhImgWS img, GhBinWS bin, cudaStream_t stream);
+int gh_launch_tile_sort(int T, unsigned int max_tile_len, long long R, GhImgWS img, GhBinWS bin, cudaStream_t stream);
 
 void gh_launch_blend_forward(int W, int H, int gx, int gy, GhGeomWS geom, GhImgWS img, GhBinWS bin,
                              const float* features, const float* bg, float* out_color,
