@@ -161,6 +161,7 @@ def main():
         dist.init_process_group("nccl", device_id=device)
 
     from gaussianhaircut_b200 import synth
+    from gaussianhaircut_b200 import dist as ghdist
     sys.path.insert(0, os.path.join(ROOT, "oracle"))
     import build_ref
 
@@ -215,7 +216,9 @@ def main():
         if arena:
             flat, grads, _ = mod.rasterize_gaussians_backward_arena(*bw)
             if use_dist:
-                dist.all_reduce(flat, op=dist.ReduceOp.SUM)     # one collective per step over the whole arena
+                # one collective per step, over the part of the arena the optimizer reads
+                dist.all_reduce(ghdist.trainable_slice(flat, P, "native" if args.mode == "native" else "any"),
+                                op=dist.ReduceOp.SUM)
             last["grads"] = flat
             last["views"] = grads
         else:

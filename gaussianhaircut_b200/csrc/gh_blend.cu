@@ -125,22 +125,6 @@ __device__ __forceinline__ uint32_t gh_block_mask(const float4 g0, const float4 
     return mask;
 }
 
-// Build the per-block instance lists of one staged chunk: warp w scan-converts Gaussians
-// [32w, 32w+32) of the chunk (one per lane) and transposes the 32 masks with 32 ballots.
-__device__ __forceinline__ void gh_build_lists(GhStage& st, int buf, int cnt, int warp, int lane,
-                                               float tx0, float ty0) {
-    const int j = warp * 32 + lane;
-    uint32_t m = 0;
-    if (j < cnt) m = gh_block_mask(st.g0[buf][j], st.g1[buf][j], tx0, ty0);
-    uint32_t mine = 0;
-#pragma unroll
-    for (int k = 0; k < 32; k++) {
-        const uint32_t v = __ballot_sync(0xffffffffu, (m >> k) & 1u);
-        if (lane == k) mine = v;
-    }
-    st.bits[lane][warp] = mine;   // block `lane`, word `warp`
-}
-
 // Per-PIXEL instance lists of one staged chunk (forward pass).  Warp w scan-converts Gaussians
 // [32w, 32w+32) of the chunk (one per lane): on every pixel row the exact-conservative x-span of
 // {alpha >= 1/255} (same quadratic as gh_block_mask) becomes a 16-bit column mask; two rows form the
@@ -345,6 +329,46 @@ gh_blend_forward_kernel(const uint2* __restrict__ ranges, uint64_t* inst,
 }
 
 // ------------------------------------------------------------------------------------------ backward
+// Backward staging: ONE window of GH_BWD_CHUNK instances (single-buffered; the other resident CTAs of
+// the SM cover the gather latency).  The 8 blocks of a warp walk their lists in lock-step, so a warp
+// spends max(list length over its blocks) steps per window: a 512-wide window wastes fewer lanes on
+// that maximum than two 256-wide ones (tools/imbalance.py: 0.74 vs 0.69 lane efficiency at 500k).
+#define GH_BWD_CHUNK 512
+
+struct GhStageB {
+    float4 g0[GH_BWD_CHUNK];
+    float4 g1[GH_BWD_CHUNK];
+    float2 feat[GH_BWD_CHUNK * GH_HALF_C];
+    uint32_t id[GH_BWD_CHUNK];
+    uint32_t bits[32][GH_BWD_CHUNK / 32 + 1];   // [block][word]; +1 pad against bank conflicts
+};
+
+__device__ __forceinline__ void gh_stage_issue_b(GhStageB& st, int slot, uint32_t id,
+                                                 const GhGeo* __restrict__ geo, const float* __restrict__ features) {
+    const float4* gp = reinterpret_cast<const float4*>(geo + id);
+    gh_cp_async16(&st.g0[slot], gp);
+    gh_cp_async16(&st.g1[slot], gp + 1);
+    const float2* fp = reinterpret_cast<const float2*>(features + (size_t)id * GH_NUM_CHANNELS);
+#pragma unroll
+    for (int k = 0; k < GH_HALF_C; k++) gh_cp_async8(&st.feat[slot * GH_HALF_C + k], fp + k);
+    st.id[slot] = id;
+}
+
+// batch `word` = instances [32 word, 32 word + 32) of the window, one per lane; 32 ballots transpose
+// the 32 block masks into one list word per block
+__device__ __forceinline__ void gh_build_lists_b(GhStageB& st, int cnt, int word, int lane, float tx0, float ty0) {
+    const int j = word * 32 + lane;
+    uint32_t m = 0;
+    if (j < cnt) m = gh_block_mask(st.g0[j], st.g1[j], tx0, ty0);
+    uint32_t mine = 0;
+#pragma unroll
+    for (int k = 0; k < 32; k++) {
+        const uint32_t v = __ballot_sync(0xffffffffu, (m >> k) & 1u);
+        if (lane == k) mine = v;
+    }
+    st.bits[lane][word] = mine;
+}
+
 // CTA = tile = 4 warps.  A lane owns a vertical pixel pair (x, y0), (x, y0+1); 4 lanes own a 4x2 block;
 // the 8 blocks of a warp walk their own lists in lock-step, i.e. every warp instruction works on EIGHT
 // different Gaussians.  The two pixels of a lane are summed in registers; the 16 gradient components
@@ -436,20 +460,94 @@ gh_blend_backward_kernel(const uint2* __restrict__ ranges, const uint64_t* __res
                          const float* __restrict__ dL_dpix,
                          float* __restrict__ acc16)   // [P][16]: colors 0..9, mean2D x,y, conic x,y,w, opacity
 {
-    __shared__ GhStage st;
+    __shared__ GhStageB st;
     __shared__ uint32_t s_warp_last[GH_BWD_THREADS / 32];
+    __shared__ uint32_t s_glast[32];                       // per block: deepest list position any of its pixels blended
+    __shared__ uint8_t s_perm[GH_BWD_THREADS / 32][32];    // per warp (redundant copies): rank -> block
 
     const int tile = blockIdx.x;
     const int tx = tile % gx, ty = tile / gx;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int blk = 8 * warp + (lane >> 2);           // block = 4 lanes; bx = blk & 3, by = blk >> 2
-    const int px = tx * GH_BLOCK_X + 4 * (blk & 3) + (lane & 3);
-    const int py0 = ty * GH_BLOCK_Y + 2 * (blk >> 2);
-    const float pxf = (float)px;
     const float tx0 = (float)(tx * GH_BLOCK_X), ty0 = (float)(ty * GH_BLOCK_Y);
     const unsigned gshift = lane & 28;
     const size_t plane = (size_t)H * W;
     const uint2 rg = ranges[tile];
+
+    // ---- how far do the blocks / the tile reach into the list?  (natural block order here)
+    {
+        const int nb = 8 * warp + (lane >> 2);
+        const int nx = tx * GH_BLOCK_X + 4 * (nb & 3) + (lane & 3);
+        const int ny = ty * GH_BLOCK_Y + 2 * (nb >> 2);
+        uint32_t gl = 0;
+        if (nx < W && ny < H) gl = n_contrib[(size_t)ny * W + nx];
+        if (nx < W && ny + 1 < H) gl = max(gl, n_contrib[(size_t)(ny + 1) * W + nx]);
+        gl = max(gl, __shfl_xor_sync(0xffffffffu, gl, 2));
+        gl = max(gl, __shfl_xor_sync(0xffffffffu, gl, 1));
+        if ((lane & 3) == 0) s_glast[nb] = gl;
+        uint32_t wl = gl;
+#pragma unroll
+        for (int o = 4; o < 32; o <<= 1) wl = max(wl, __shfl_xor_sync(0xffffffffu, wl, o));
+        if (lane == 0) s_warp_last[warp] = wl;
+    }
+    __syncthreads();
+    uint32_t tile_last = 0;
+#pragma unroll
+    for (int w = 0; w < GH_BWD_THREADS / 32; w++) tile_last = max(tile_last, s_warp_last[w]);
+    const int n = (int)tile_last;             // nothing beyond is blended by any pixel of this tile
+    const int nchunks = (n + GH_BWD_CHUNK - 1) / GH_BWD_CHUNK;
+    if (nchunks == 0) return;
+    constexpr int PER_THREAD = GH_BWD_CHUNK / GH_BWD_THREADS;
+
+    // ---- stage the last window (windows are visited last to first) and build its lists
+    uint32_t next_id[PER_THREAD];
+    {
+        const int base = (nchunks - 1) * GH_BWD_CHUNK;
+        const int cnt = n - base;
+#pragma unroll
+        for (int h = 0; h < PER_THREAD; h++) {
+            const int slot = tid + h * GH_BWD_THREADS;
+            if (slot < cnt) gh_stage_issue_b(st, slot, (uint32_t)inst[(size_t)rg.x + base + slot], geo, features);
+        }
+        gh_cp_async_commit();
+        if (nchunks > 1) {
+#pragma unroll
+            for (int h = 0; h < PER_THREAD; h++)
+                next_id[h] = (uint32_t)inst[(size_t)rg.x + base - GH_BWD_CHUNK + tid + h * GH_BWD_THREADS];
+        }
+        gh_cp_async_wait_all();
+        __syncthreads();
+        for (int word = warp; word * 32 < cnt; word += GH_BWD_THREADS / 32)
+            gh_build_lists_b(st, cnt, word, lane, tx0, ty0);
+        __syncthreads();
+    }
+
+    // ---- block -> (warp, quarter-warp) assignment.  The 8 blocks of a warp advance in lock-step, so a
+    // warp pays for its LONGEST list: blocks are ranked by the length of their list in the window just
+    // built (lane b counts block b; every warp computes the same ranking for itself) and each warp
+    // takes 8 neighbours of that ranking.  Any assignment gives the same gradients up to the order of
+    // the float atomics.
+    int blk;
+    {
+        const int base = (nchunks - 1) * GH_BWD_CHUNK;
+        const int nw = (n - base + 31) >> 5;
+        const uint32_t gl = s_glast[lane];
+        uint32_t len = 0;
+        for (int w = 0; w < nw; w++) {
+            const int lim = (int)gl - (base + w * 32);
+            const uint32_t valid = lim >= 32 ? 0xffffffffu : (lim <= 0 ? 0u : ((1u << lim) - 1u));
+            len += __popc(st.bits[lane][w] & valid);
+        }
+        const uint32_t key = (len << 5) | (uint32_t)lane;
+        int rank = 0;
+#pragma unroll
+        for (int k = 0; k < 32; k++) rank += (__shfl_sync(0xffffffffu, key, k) < key) ? 1 : 0;
+        s_perm[warp][rank] = (uint8_t)lane;
+        __syncwarp();
+        blk = s_perm[warp][8 * warp + (lane >> 2)];
+    }
+    const int px = tx * GH_BLOCK_X + 4 * (blk & 3) + (lane & 3);
+    const int py0 = ty * GH_BLOCK_Y + 2 * (blk >> 2);
+    const float pxf = (float)px;
 
     GhBwdPix pix[2];
 #pragma unroll
@@ -473,60 +571,34 @@ gh_blend_backward_kernel(const uint2* __restrict__ ranges, const uint64_t* __res
     // pixel-coordinate -> NDC chain rule factors (backward.cu:464-465)
     const float ddelx_dx = 0.5f * W, ddely_dy = 0.5f * H;
 
-    // how far does this block / warp / tile reach into the list?
-    uint32_t glast = max(pix[0].last, pix[1].last);
-    glast = max(glast, __shfl_xor_sync(0xffffffffu, glast, 2));
-    glast = max(glast, __shfl_xor_sync(0xffffffffu, glast, 1));
+    const uint32_t glast = s_glast[blk];
     uint32_t wlast = glast;
 #pragma unroll
     for (int o = 4; o < 32; o <<= 1) wlast = max(wlast, __shfl_xor_sync(0xffffffffu, wlast, o));
-    if (lane == 0) s_warp_last[warp] = wlast;
-    __syncthreads();
-    uint32_t tile_last = 0;
-#pragma unroll
-    for (int w = 0; w < GH_BWD_THREADS / 32; w++) tile_last = max(tile_last, s_warp_last[w]);
-    const int n = (int)tile_last;             // nothing beyond is blended by any pixel of this tile
-    const int nchunks = (n + GH_CHUNK - 1) / GH_CHUNK;
-
-    // chunks are visited last to first; every thread stages 2 instances; prologue stages the last chunk
-    uint32_t next_id[2] = {0u, 0u};
-    if (nchunks > 0) {
-        const int b0 = (nchunks - 1) * GH_CHUNK;
-#pragma unroll
-        for (int h = 0; h < 2; h++) {
-            const int slot = tid + h * GH_BWD_THREADS;
-            if (b0 + slot < n) gh_stage_issue(st, (nchunks - 1) & 1, slot, (uint32_t)inst[(size_t)rg.x + b0 + slot], geo, features);
-        }
-        gh_cp_async_commit();
-        if (nchunks > 1) {
-#pragma unroll
-            for (int h = 0; h < 2; h++) next_id[h] = (uint32_t)inst[(size_t)rg.x + b0 - GH_CHUNK + tid + h * GH_BWD_THREADS];
-        }
-    }
 
     for (int c = nchunks - 1; c >= 0; c--) {
-        const int buf = c & 1;
-        const int base = c * GH_CHUNK;
-        const int cnt = min(GH_CHUNK, n - base);
-        gh_cp_async_wait_all();
-        __syncthreads();
-        if (c > 0) {
+        const int base = c * GH_BWD_CHUNK;
+        const int cnt = min(GH_BWD_CHUNK, n - base);
+        if (c != nchunks - 1) {
+            __syncthreads();                       // everyone is done with the previous window
 #pragma unroll
-            for (int h = 0; h < 2; h++) gh_stage_issue(st, buf ^ 1, tid + h * GH_BWD_THREADS, next_id[h], geo, features);
+            for (int h = 0; h < PER_THREAD; h++) gh_stage_issue_b(st, tid + h * GH_BWD_THREADS, next_id[h], geo, features);
             gh_cp_async_commit();
-            if (c > 1) {
+            if (c > 0) {
 #pragma unroll
-                for (int h = 0; h < 2; h++)
-                    next_id[h] = (uint32_t)inst[(size_t)rg.x + base - 2 * GH_CHUNK + tid + h * GH_BWD_THREADS];
+                for (int h = 0; h < PER_THREAD; h++)
+                    next_id[h] = (uint32_t)inst[(size_t)rg.x + base - GH_BWD_CHUNK + tid + h * GH_BWD_THREADS];
             }
+            gh_cp_async_wait_all();
+            __syncthreads();
+            // per-block lists: each of the 4 warps scan-converts every fourth batch of 32 Gaussians
+            for (int word = warp; word * 32 < cnt; word += GH_BWD_THREADS / 32)
+                gh_build_lists_b(st, cnt, word, lane, tx0, ty0);
+            __syncthreads();
         }
-        // per-block lists: each of the 4 warps scan-converts two batches of 32 Gaussians
-        gh_build_lists(st, buf, cnt, warp, lane, tx0, ty0);
-        gh_build_lists(st, buf, cnt, warp + 4, lane, tx0, ty0);
-        __syncthreads();
         if ((uint32_t)base >= wlast) continue;
 
-        int wi = GH_CHUNK / 32;
+        int wi = (cnt + 31) >> 5;
         uint32_t cur = 0;
         while (true) {
             while (cur == 0 && wi > 0) {
@@ -543,9 +615,9 @@ gh_blend_backward_kernel(const uint2* __restrict__ ranges, const uint64_t* __res
             const int bpos = act ? 31 - __clz(cur) : 0;   // back to front
             cur &= ~(1u << bpos);
             const int jj = act ? wi * 32 + bpos : 0;
-            const uint32_t id = st.id[buf][jj];
-            const float4 g0 = st.g0[buf][jj], g1 = st.g1[buf][jj];
-            const float2* feat = &st.feat[buf][jj * GH_HALF_C];
+            const uint32_t id = st.id[jj];
+            const float4 g0 = st.g0[jj], g1 = st.g1[jj];
+            const float2* feat = &st.feat[jj * GH_HALF_C];
             const uint32_t pos = act ? (uint32_t)(base + jj) : 0xffffffffu;
             float v[16];
             const bool c0 = gh_bwd_pixel<true>(pix[0], g0, g1, feat, pxf, pos, ddelx_dx, ddely_dy, v);

@@ -33,9 +33,23 @@ def epoch_schedule(world_size: int, num_cameras: int) -> List[List[int]]:
     return [[views_for_step(s, r, world_size, num_cameras) for r in range(world_size)] for s in range(steps)]
 
 
+def trainable_slice(flat: torch.Tensor, num_gaussians: int, call_shape: str = "native") -> torch.Tensor:
+    """The contiguous prefix of the gradient arena that the optimizer consumes.
+
+    `native` (the op computes covariances from scales/rotations): rotations, colors, opacity,
+    means2D, means3D, scales = the first 24 floats per Gaussian; the conic / cov3D segments behind
+    it stay zero and need not travel.  Any other call shape: the whole arena.
+    """
+    from . import _C
+    if call_shape == "native":
+        return flat[: num_gaussians * _C.GRAD_FLOATS_TRAINABLE_NATIVE]
+    return flat
+
+
 def allreduce_gradient_arena(flat: torch.Tensor, group: Optional[dist.ProcessGroup] = None,
                              average: bool = False, async_op: bool = False):
-    """Sum (or mean) the flat gradient arena over all ranks with a single collective.
+    """Sum (or mean) the flat gradient arena (or a `trainable_slice` of it) over all ranks with a
+    single collective.
 
     No-op when torch.distributed is not initialised or the world has one rank.  With
     `async_op=True` returns the work handle so the caller can overlap the next view's forward.

@@ -138,6 +138,9 @@ def test_grad_arena_layout():
     assert flat.numel() == P * 34 and _C.GRAD_FLOATS_PER_GAUSSIAN == 34
     assert g["rotations"].data_ptr() % 16 == 0          # stored as one float4 per Gaussian
     shapes = {"rotations": 4, "conic": 4, "colors": 10, "cov3D": 6, "means3D": 3, "means2D": 3, "scales": 3, "opacity": 1}
+    assert (g["conic"].data_ptr() - flat.data_ptr()) % 16 == 0 and g["rotations"].data_ptr() == flat.data_ptr()
+    assert _C.GRAD_FLOATS_TRAINABLE_NATIVE == 24
+    assert g["conic"].data_ptr() - flat.data_ptr() == 24 * P * 4
     seen = 0
     for k, n in shapes.items():
         assert tuple(g[k].shape) == (P, n)
@@ -207,7 +210,7 @@ gd.allreduce_gradient_arena(flat)                      # ONE collective for ever
 gathered = [torch.zeros_like(mine) for _ in range(world)]
 dist.all_gather(gathered, mine)
 assert torch.allclose(flat, sum(gathered)), "arena all-reduce != sum of per-rank gradients"
-assert torch.allclose(g["colors"], sum(x[8 * P:18 * P].view(P, 10) for x in gathered))   # views see the result
+assert torch.allclose(g["colors"], sum(x[4 * P:14 * P].view(P, 10) for x in gathered))   # views see the result
 acc, den, mx = torch.full((P, 1), float(rank + 1)), torch.ones(P, 1), torch.full((P,), float(rank))
 gd.allreduce_densification_stats(acc, den, mx)
 assert float(acc[0]) == sum(range(1, world + 1)) and float(den[0]) == world and float(mx[0]) == world - 1
