@@ -81,50 +81,6 @@ __device__ __forceinline__ void gh_stage_issue(GhStage& st, int buf, int slot, u
     st.id[buf][slot] = id;
 }
 
-// Which of the tile's 32 blocks (4 wide x 2 high; bit = by*4 + bx) can this Gaussian reach with
-// alpha >= 1/255?  Exact-conservative: on each pixel row the set {q(d) <= 2(thr+slack)} is an
-// x-interval obtained from the quadratic; the interval is widened by 0.01 px and rounded outwards to
-// whole pixels.  Returns all ones when the conic is not positive definite (no bound available).
-// Skipping a Gaussian in a block whose bit is clear cannot change any pixel of that block: each of
-// them would take the reference's `alpha < 1/255 -> continue` (forward.cu:370, backward.cu:503).
-__device__ __forceinline__ uint32_t gh_block_mask(const float4 g0, const float4 g1, float tx0, float ty0) {
-    const float gx = g0.x, gy = g0.y, a = g0.z, b = g0.w, c = g1.x, thr = g1.z, pd = g1.w;
-    if (pd == 0.f) return 0xffffffffu;
-    const float mxd = fmaxf(fabsf(gx - tx0), fabsf(gx - (tx0 + 15.f)));
-    const float myd = fmaxf(fabsf(gy - ty0), fabsf(gy - (ty0 + 15.f)));
-    const float slack = 1e-3f + 2e-5f * (a * mxd * mxd + c * myd * myd + 2.f * fabsf(b) * mxd * myd);
-    const float Q = 2.f * (thr + slack);
-    if (!(Q >= 0.f)) return (Q != Q) ? 0xffffffffu : 0u;
-    const float ia = __frcp_rn(a);
-    const float aQ = a * Q;
-    const float bbac = b * b - a * c;      // <= 0 for a PD conic
-    uint32_t mask = 0;
-#pragma unroll
-    for (int by = 0; by < 8; by++) {
-        float xlo = 1e30f, xhi = -1e30f;
-#pragma unroll
-        for (int r = 0; r < 2; r++) {
-            const float dy = gy - (ty0 + (float)(2 * by + r));
-            // a dx^2 + 2 b dy dx + (c dy^2 - Q) <= 0,  dx = gx - px
-            const float disc = fmaf(dy * dy, bbac, aQ);
-            if (disc > 0.f) {
-                const float s = disc * rsqrtf(disc);
-                const float hb = b * dy;
-                xlo = fminf(xlo, gx + (hb - s) * ia);
-                xhi = fmaxf(xhi, gx + (hb + s) * ia);
-            }
-        }
-        // tile-local integer pixel columns inside [xlo - .01, xhi + .01]
-        const float lo = (xlo - 0.01f) - tx0, hi = (xhi + 0.01f) - tx0;
-        const int p0 = max(0, __float2int_ru(lo)), p1 = min(15, __float2int_rd(hi));
-        if (p0 <= p1) {
-            const int b0 = p0 >> 2, b1 = p1 >> 2;
-            mask |= (((2u << (b1 - b0)) - 1u) << b0) << (4 * by);
-        }
-    }
-    return mask;
-}
-
 // Per-PIXEL instance lists of one staged chunk (forward pass).  Warp w scan-converts Gaussians
 // [32w, 32w+32) of the chunk (one per lane): on every pixel row the exact-conservative x-span of
 // {alpha >= 1/255} (same quadratic as gh_block_mask) becomes a 16-bit column mask; two rows form the
@@ -233,9 +189,9 @@ gh_blend_forward_kernel(const uint2* __restrict__ ranges, uint64_t* inst,
     const int nchunks = (n + GH_CHUNK - 1) / GH_CHUNK;
 
     float T = 1.0f;
-    float C[GH_NUM_CHANNELS];
+    float2 C2[GH_HALF_C];                      // channel pairs (2k, 2k+1)
 #pragma unroll
-    for (int ch = 0; ch < GH_NUM_CHANNELS; ch++) C[ch] = 0.f;
+    for (int k = 0; k < GH_HALF_C; k++) C2[k] = make_float2(0.f, 0.f);
     uint32_t last = 0;
     bool done = !inside;
     bool warp_done = (__ballot_sync(0xffffffffu, done) == 0xffffffffu);
@@ -302,12 +258,13 @@ gh_blend_forward_kernel(const uint2* __restrict__ ranges, uint64_t* inst,
                 if (e.ok) {
                     const float test_T = GH_MUL(T, GH_SUB(1.0f, e.alpha));
                     if (test_T < 0.0001f) { done = true; break; }
+                    // C[ch] = fma(T, alpha * f[ch], C[ch]) (forward.cu:379-380 as ptxas fuses it), two
+                    // channels per instruction with Blackwell's packed FP32 pipe: FMUL2 + FFMA2 round each
+                    // half exactly like FMUL + FFMA
+                    const float2 a2 = make_float2(e.alpha, e.alpha), T2 = make_float2(T, T);
 #pragma unroll
-                    for (int k = 0; k < GH_HALF_C; k++) {
-                        const float2 f = st.feat[buf][jj * GH_HALF_C + k];
-                        C[2 * k + 0] = GH_FMA(T, GH_MUL(e.alpha, f.x), C[2 * k + 0]);
-                        C[2 * k + 1] = GH_FMA(T, GH_MUL(e.alpha, f.y), C[2 * k + 1]);
-                    }
+                    for (int k = 0; k < GH_HALF_C; k++)
+                        C2[k] = __ffma2_rn(T2, __fmul2_rn(a2, st.feat[buf][jj * GH_HALF_C + k]), C2[k]);
                     T = test_T;
                     last = (uint32_t)(base + jj + 1);
                 }
@@ -324,7 +281,7 @@ gh_blend_forward_kernel(const uint2* __restrict__ ranges, uint64_t* inst,
         const size_t plane = (size_t)H * W;
 #pragma unroll
         for (int ch = 0; ch < GH_NUM_CHANNELS; ch++)
-            out[ch * plane + pix] = GH_FMA(T, __ldg(bg + ch), C[ch]);
+            out[ch * plane + pix] = GH_FMA(T, __ldg(bg + ch), (ch & 1) ? C2[ch >> 1].y : C2[ch >> 1].x);
     }
 }
 
@@ -354,19 +311,72 @@ __device__ __forceinline__ void gh_stage_issue_b(GhStageB& st, int slot, uint32_
     st.id[slot] = id;
 }
 
-// batch `word` = instances [32 word, 32 word + 32) of the window, one per lane; 32 ballots transpose
-// the 32 block masks into one list word per block
-__device__ __forceinline__ void gh_build_lists_b(GhStageB& st, int cnt, int word, int lane, float tx0, float ty0) {
+// Packed FP32 (Blackwell FFMA2 / FMUL2 / FADD2: two IEEE-rounded results per issue slot).  The blend
+// kernels are bound by instruction issue, not by the FP32 pipe, so pairing halves their FP32 cost.
+__device__ __forceinline__ float2 gh_f2(float a) { return make_float2(a, a); }
+__device__ __forceinline__ float2 gh_neg2(float2 a) { return make_float2(-a.x, -a.y); }
+__device__ __forceinline__ float2 gh_mul2(float2 a, float2 b) { return __fmul2_rn(a, b); }
+__device__ __forceinline__ float2 gh_add2(float2 a, float2 b) { return __fadd2_rn(a, b); }
+__device__ __forceinline__ float2 gh_sub2(float2 a, float2 b) { return __fadd2_rn(a, gh_neg2(b)); }
+__device__ __forceinline__ float2 gh_fma2(float2 a, float2 b, float2 c) { return __ffma2_rn(a, b, c); }
+__device__ __forceinline__ float gh_rcp_approx(float x) {
+    float r;
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+    return r;
+}
+
+// Which of the tile's 32 blocks (4 wide x 2 high; bit = by*4 + bx) can this Gaussian reach with
+// alpha >= 1/255?  Exact-conservative: on each pixel row the set {q(d) <= 2(thr+slack)} is an
+// x-interval obtained from the quadratic; the interval is widened by 0.01 px and rounded outwards to
+// whole pixels.  Returns all ones when the conic is not positive definite (no bound available).
+// Skipping a Gaussian in a block whose bit is clear cannot change any pixel of that block: each of
+// them would take the reference's `alpha < 1/255 -> continue` (forward.cu:370, backward.cu:503).
+// Two pixel rows per instruction; a row without a real span has disc <= 0 -> s = NaN -> fminf / fmaxf
+// ignore it.
+__device__ __forceinline__ uint32_t gh_block_mask2(const float4 g0, const float4 g1, float tx0, float ty0) {
+    const float gx = g0.x, gy = g0.y, a = g0.z, b = g0.w, c = g1.x, thr = g1.z, pd = g1.w;
+    if (pd == 0.f) return 0xffffffffu;
+    const float mxd = fmaxf(fabsf(gx - tx0), fabsf(gx - (tx0 + 15.f)));
+    const float myd = fmaxf(fabsf(gy - ty0), fabsf(gy - (ty0 + 15.f)));
+    const float slack = 1e-3f + 2e-5f * (a * mxd * mxd + c * myd * myd + 2.f * fabsf(b) * mxd * myd);
+    const float Q = 2.f * (thr + slack);
+    if (!(Q >= 0.f)) return (Q != Q) ? 0xffffffffu : 0u;
+    const float2 ia = gh_f2(__frcp_rn(a)), aQ = gh_f2(a * Q), bbac = gh_f2(b * b - a * c), gx2 = gh_f2(gx), b2 = gh_f2(b);
+    float2 dy = make_float2(gy - ty0, gy - (ty0 + 1.f));     // rows 2 by, 2 by + 1
+    uint32_t mask = 0;
+#pragma unroll
+    for (int by = 0; by < 8; by++) {
+        // a dx^2 + 2 b dy dx + (c dy^2 - Q) <= 0,  dx = gx - px
+        const float2 disc = gh_fma2(gh_mul2(dy, dy), bbac, aQ);
+        const float2 s = gh_mul2(disc, make_float2(rsqrtf(disc.x), rsqrtf(disc.y)));   // NaN unless disc > 0
+        const float2 hb = gh_mul2(b2, dy);
+        const float2 lo2 = gh_fma2(gh_sub2(hb, s), ia, gx2), hi2 = gh_fma2(gh_add2(hb, s), ia, gx2);
+        const float xlo = fminf(fminf(1e30f, lo2.x), lo2.y), xhi = fmaxf(fmaxf(-1e30f, hi2.x), hi2.y);
+        // tile-local integer pixel columns inside [xlo - .01, xhi + .01]
+        const float lo = (xlo - 0.01f) - tx0, hi = (xhi + 0.01f) - tx0;
+        const int p0 = max(0, __float2int_ru(lo)), p1 = min(15, __float2int_rd(hi));
+        if (p0 <= p1) {
+            const int b0 = p0 >> 2, b1 = p1 >> 2;
+            mask |= (((2u << (b1 - b0)) - 1u) << b0) << (4 * by);
+        }
+        dy = gh_add2(dy, gh_f2(-2.f));
+    }
+    return mask;
+}
+
+// batch `word` = instances [32 word, 32 word + 32) of the window, one per lane; a 5-step shuffle
+// transpose turns the 32 block masks into one list word per block (lane = block).  The word is cut at
+// the block's deepest blended list position `glast` here, once, rather than in the traversal loop.
+__device__ __forceinline__ void gh_build_lists_b(GhStageB& st, int cnt, int word, int lane, float tx0, float ty0,
+                                                 int base, uint32_t glast_of_lane_block) {
     const int j = word * 32 + lane;
     uint32_t m = 0;
-    if (j < cnt) m = gh_block_mask(st.g0[j], st.g1[j], tx0, ty0);
+    if (j < cnt) m = gh_block_mask2(st.g0[j], st.g1[j], tx0, ty0);
     uint32_t mine = 0;
-#pragma unroll
-    for (int k = 0; k < 32; k++) {
-        const uint32_t v = __ballot_sync(0xffffffffu, (m >> k) & 1u);
-        if (lane == k) mine = v;
-    }
-    st.bits[lane][word] = mine;
+    if (__any_sync(0xffffffffu, m != 0u)) mine = gh_transpose32(m, lane);
+    const int lim = (int)glast_of_lane_block - (base + word * 32);
+    const uint32_t valid = lim >= 32 ? 0xffffffffu : (lim <= 0 ? 0u : ((1u << lim) - 1u));
+    st.bits[lane][word] = mine & valid;
 }
 
 // CTA = tile = 4 warps.  A lane owns a vertical pixel pair (x, y0), (x, y0+1); 4 lanes own a 4x2 block;
@@ -377,79 +387,98 @@ __device__ __forceinline__ void gh_build_lists_b(GhStageB& st, int cnt, int word
 #define GH_BWD_THREADS 128
 
 __device__ __forceinline__ float4 gh_group4_reduce16(const float (&v)[16], int lane) {
-    float w8[8], w4[4];
+    float w8[8];
     const bool b1 = lane & 2, b0 = lane & 1;
 #pragma unroll
-    for (int i = 0; i < 8; i++) {
-        const float send = b1 ? v[i] : v[i + 8];
-        const float keep = b1 ? v[i + 8] : v[i];
-        w8[i] = keep + __shfl_xor_sync(0xffffffffu, send, 2);
+    for (int i = 0; i < 8; i += 2) {
+        const float s0 = b1 ? v[i] : v[i + 8], s1 = b1 ? v[i + 1] : v[i + 9];
+        const float k0 = b1 ? v[i + 8] : v[i], k1 = b1 ? v[i + 9] : v[i + 1];
+        const float2 r = gh_add2(make_float2(k0, k1), make_float2(__shfl_xor_sync(0xffffffffu, s0, 2),
+                                                                  __shfl_xor_sync(0xffffffffu, s1, 2)));
+        w8[i] = r.x; w8[i + 1] = r.y;
     }
+    float2 q[2];
 #pragma unroll
-    for (int i = 0; i < 4; i++) {
-        const float send = b0 ? w8[i] : w8[i + 4];
-        const float keep = b0 ? w8[i + 4] : w8[i];
-        w4[i] = keep + __shfl_xor_sync(0xffffffffu, send, 1);
+    for (int i = 0; i < 4; i += 2) {
+        const float s0 = b0 ? w8[i] : w8[i + 4], s1 = b0 ? w8[i + 1] : w8[i + 5];
+        const float k0 = b0 ? w8[i + 4] : w8[i], k1 = b0 ? w8[i + 5] : w8[i + 1];
+        q[i >> 1] = gh_add2(make_float2(k0, k1), make_float2(__shfl_xor_sync(0xffffffffu, s0, 1),
+                                                             __shfl_xor_sync(0xffffffffu, s1, 1)));
     }
-    return make_float4(w4[0], w4[1], w4[2], w4[3]);   // components 4*(lane&3) + {0,1,2,3}
+    return make_float4(q[0].x, q[0].y, q[1].x, q[1].y);   // components 4*(lane&3) + {0,1,2,3}
 }
 
-struct GhBwdPix {
-    float T, A, last_alpha, last_cdot, T_final, bg_dot, pyf;
-    uint32_t last;
-    float dL[GH_NUM_CHANNELS];
+// State of the lane's pixel pair; .x = pixel (x, y0), .y = pixel (x, y0 + 1).
+struct GhBwdPair {
+    float2 T, A, last_alpha, last_cdot;
+    float2 ntf_bg;                 // -T_final * (bg . dL_dpix)
+    float2 npy;                    // -(pixel y)
+    uint32_t last0, last1;
+    float2 dL0[GH_HALF_C], dL1[GH_HALF_C];   // dL/dpixel of pixel 0 / pixel 1, channel pairs (2k, 2k+1)
 };
 
-// One pixel's share of one Gaussian, branch-free: every lane runs the same instruction stream and a
-// pixel that does not blend this Gaussian (behind its last contributor, power > 0, alpha < 1/255 --
-// the reference's three `continue`s, backward.cu:490-505) contributes exact zeros and keeps its state.
-// FIRST = true assigns v, false accumulates into it (the two pixels of a lane are summed in registers).
-template <bool FIRST>
-__device__ __forceinline__ bool gh_bwd_pixel(GhBwdPix& p, const float4 g0, const float4 g1, const float2* feat,
-                                             float pxf, uint32_t pos, float ddelx_dx, float ddely_dy, float (&v)[16]) {
-    const float dx = GH_SUB(g0.x, pxf), dy = GH_SUB(g0.y, p.pyf);
-    const float power = gh_power(dx, dy, g0.z, g0.w, g1.x);
-    const float Gx = expf((power > 0.0f) ? 0.0f : power);      // expf(power) whenever the reference evaluates it
-    const float alpha = fminf(0.99f, GH_MUL(g1.y, Gx));
-    const bool ok = (pos < p.last) & !(power > 0.0f) & !(alpha < 1.0f / 255.0f);
-    const float am = ok ? alpha : 0.f;
-    const float G = ok ? Gx : 0.f;
-    // T_{before this Gaussian} = T / (1 - alpha); gradients only need ~1 ulp here, so one fast reciprocal
-    const float r = __fdividef(1.0f, 1.0f - am);              // exactly 1 when am == 0
-    p.T *= r;
-    const float w = am * p.T;                                  // d(out)/d(color)
-    float cdot = 0.f;
+// The pixel pair's share of one Gaussian, branch-free: every lane runs the same instruction stream and
+// a pixel that does not blend this Gaussian (behind its last contributor, power > 0, alpha < 1/255 --
+// the reference's three `continue`s, backward.cu:490-505) has alpha = G = 0, contributes exact zeros
+// and keeps its state.  power / alpha are bit-identical to the forward pass (same operation order,
+// FMUL2/FFMA2 round like FMUL/FFMA), so both passes agree on which pixels blend.  v = the 16 gradient
+// components summed over the two pixels.
+__device__ __forceinline__ bool gh_bwd_pair(GhBwdPair& p, const float4 g0, const float4 g1, const float2* feat,
+                                            float pxf, uint32_t pos, float ddelx_dx, float ddely_dy, float (&v)[16]) {
+    const float dx = GH_SUB(g0.x, pxf);
+    const float2 dx2 = gh_f2(dx);
+    const float2 dy = gh_add2(gh_f2(g0.y), p.npy);
+    // gh_power: fma(fma(dx, dx*ca, dy*(dy*cc)), -0.5, -(dy*(dx*cb)))
+    const float t1 = GH_MUL(dx, g0.z), dxcb = GH_MUL(dx, g0.w);
+    const float2 t3 = gh_mul2(dy, gh_mul2(dy, gh_f2(g1.x)));
+    const float2 sq = gh_fma2(dx2, gh_f2(t1), t3);
+    const float2 power = gh_fma2(sq, gh_f2(-0.5f), gh_mul2(dy, gh_f2(-dxcb)));
+    const float Gx0 = expf((power.x > 0.0f) ? 0.0f : power.x);   // expf(power) whenever the reference evaluates it
+    const float Gx1 = expf((power.y > 0.0f) ? 0.0f : power.y);
+    const float2 ao = gh_mul2(gh_f2(g1.y), make_float2(Gx0, Gx1));
+    const float alpha0 = fminf(0.99f, ao.x), alpha1 = fminf(0.99f, ao.y);
+    const bool ok0 = (pos < p.last0) & !(power.x > 0.0f) & !(alpha0 < 1.0f / 255.0f);
+    const bool ok1 = (pos < p.last1) & !(power.y > 0.0f) & !(alpha1 < 1.0f / 255.0f);
+    const float2 am = make_float2(ok0 ? alpha0 : 0.f, ok1 ? alpha1 : 0.f);
+    const float2 G = make_float2(ok0 ? Gx0 : 0.f, ok1 ? Gx1 : 0.f);
+    // T_{before this Gaussian} = T / (1 - alpha); gradients only need ~1 ulp here: MUFU.RCP, 1 - alpha
+    // is in [0.01, 1] and rcp(1) == 1 exactly
+    const float2 om = gh_sub2(gh_f2(1.0f), am);
+    const float2 r = make_float2(gh_rcp_approx(om.x), gh_rcp_approx(om.y));
+    p.T = gh_mul2(p.T, r);
+    const float2 w = gh_mul2(am, p.T);                          // d(out)/d(color)
+    const float2 w0 = gh_f2(w.x), w1 = gh_f2(w.y);
+    float2 c0, c1;
 #pragma unroll
     for (int k = 0; k < GH_HALF_C; k++) {
         const float2 f = feat[k];
-        cdot = fmaf(f.x, p.dL[2 * k], cdot);
-        cdot = fmaf(f.y, p.dL[2 * k + 1], cdot);
-        if (FIRST) {
-            v[2 * k] = w * p.dL[2 * k];
-            v[2 * k + 1] = w * p.dL[2 * k + 1];
-        } else {
-            v[2 * k] = fmaf(w, p.dL[2 * k], v[2 * k]);
-            v[2 * k + 1] = fmaf(w, p.dL[2 * k + 1], v[2 * k + 1]);
-        }
+        c0 = (k == 0) ? gh_mul2(f, p.dL0[0]) : gh_fma2(f, p.dL0[k], c0);
+        c1 = (k == 0) ? gh_mul2(f, p.dL1[0]) : gh_fma2(f, p.dL1[k], c1);
+        const float2 vc = gh_fma2(w1, p.dL1[k], gh_mul2(w0, p.dL0[k]));
+        v[2 * k] = vc.x; v[2 * k + 1] = vc.y;
     }
+    const float2 cdot = make_float2(c0.x + c0.y, c1.x + c1.y);
     // suffix recursion on the dot product (backward.cu:519-523), state advances only when blended
-    const float A_new = fmaf(p.last_alpha, p.last_cdot, (1.f - p.last_alpha) * p.A);
-    // alpha also scales how much background shows through (backward.cu:535-538)
-    float dL_dalpha = fmaf(cdot - A_new, p.T, (-p.T_final * r) * p.bg_dot);
-    dL_dalpha = ok ? dL_dalpha : 0.f;
-    p.A = ok ? A_new : p.A;
-    p.last_cdot = ok ? cdot : p.last_cdot;
-    p.last_alpha = ok ? alpha : p.last_alpha;
-    const float dL_dG = g1.y * dL_dalpha;
-    const float gdx = G * dx, gdy = G * dy;
-    const float dG_ddelx = -gdx * g0.z - gdy * g0.w;
-    const float dG_ddely = -gdy * g1.x - gdx * g0.w;
-    const float t10 = dL_dG * dG_ddelx * ddelx_dx, t11 = dL_dG * dG_ddely * ddely_dy;
-    const float hg = -0.5f * dL_dG;
-    const float t12 = hg * gdx * dx, t13 = hg * gdx * dy, t14 = hg * gdy * dy, t15 = G * dL_dalpha;
-    if (FIRST) { v[10] = t10; v[11] = t11; v[12] = t12; v[13] = t13; v[14] = t14; v[15] = t15; }
-    else { v[10] += t10; v[11] += t11; v[12] += t12; v[13] += t13; v[14] += t14; v[15] += t15; }
-    return ok;
+    const float2 A_new = gh_fma2(p.last_alpha, p.last_cdot, gh_mul2(gh_sub2(gh_f2(1.0f), p.last_alpha), p.A));
+    // alpha also scales how much background shows through (backward.cu:535-538).  Not masked: every use
+    // below is multiplied by G, which is 0 for a pixel that does not blend.
+    const float2 dL_dalpha = gh_fma2(gh_sub2(cdot, A_new), p.T, gh_mul2(p.ntf_bg, r));
+    p.A = make_float2(ok0 ? A_new.x : p.A.x, ok1 ? A_new.y : p.A.y);
+    p.last_cdot = make_float2(ok0 ? cdot.x : p.last_cdot.x, ok1 ? cdot.y : p.last_cdot.y);
+    p.last_alpha = make_float2(ok0 ? alpha0 : p.last_alpha.x, ok1 ? alpha1 : p.last_alpha.y);
+    const float2 dL_dG = gh_mul2(gh_f2(g1.y), dL_dalpha);
+    const float2 gdx = gh_mul2(G, dx2), gdy = gh_mul2(G, dy);
+    const float2 ncb = gh_f2(-g0.w);
+    const float2 dG_ddelx = gh_fma2(gdx, gh_f2(-g0.z), gh_mul2(gdy, ncb));
+    const float2 dG_ddely = gh_fma2(gdy, gh_f2(-g1.x), gh_mul2(gdx, ncb));
+    const float2 t10 = gh_mul2(dL_dG, dG_ddelx), t11 = gh_mul2(dL_dG, dG_ddely);
+    const float2 hg = gh_mul2(gh_f2(-0.5f), dL_dG);
+    const float2 hgdx = gh_mul2(hg, gdx);
+    const float2 t12 = gh_mul2(hgdx, dx2), t13 = gh_mul2(hgdx, dy), t14 = gh_mul2(gh_mul2(hg, gdy), dy);
+    const float2 t15 = gh_mul2(G, dL_dalpha);
+    v[10] = (t10.x + t10.y) * ddelx_dx; v[11] = (t11.x + t11.y) * ddely_dy;
+    v[12] = t12.x + t12.y; v[13] = t13.x + t13.y; v[14] = t14.x + t14.y; v[15] = t15.x + t15.y;
+    return ok0 | ok1;
 }
 
 __global__ void __launch_bounds__(GH_BWD_THREADS, 4)
@@ -497,6 +526,7 @@ gh_blend_backward_kernel(const uint2* __restrict__ ranges, const uint64_t* __res
     const int nchunks = (n + GH_BWD_CHUNK - 1) / GH_BWD_CHUNK;
     if (nchunks == 0) return;
     constexpr int PER_THREAD = GH_BWD_CHUNK / GH_BWD_THREADS;
+    const uint32_t glast_lane = s_glast[lane];   // the builder's lane == block after the transpose
 
     // ---- stage the last window (windows are visited last to first) and build its lists
     uint32_t next_id[PER_THREAD];
@@ -517,7 +547,7 @@ gh_blend_backward_kernel(const uint2* __restrict__ ranges, const uint64_t* __res
         gh_cp_async_wait_all();
         __syncthreads();
         for (int word = warp; word * 32 < cnt; word += GH_BWD_THREADS / 32)
-            gh_build_lists_b(st, cnt, word, lane, tx0, ty0);
+            gh_build_lists_b(st, cnt, word, lane, tx0, ty0, base, glast_lane);
         __syncthreads();
     }
 
@@ -528,15 +558,9 @@ gh_blend_backward_kernel(const uint2* __restrict__ ranges, const uint64_t* __res
     // the float atomics.
     int blk;
     {
-        const int base = (nchunks - 1) * GH_BWD_CHUNK;
-        const int nw = (n - base + 31) >> 5;
-        const uint32_t gl = s_glast[lane];
+        const int nw = (n - (nchunks - 1) * GH_BWD_CHUNK + 31) >> 5;
         uint32_t len = 0;
-        for (int w = 0; w < nw; w++) {
-            const int lim = (int)gl - (base + w * 32);
-            const uint32_t valid = lim >= 32 ? 0xffffffffu : (lim <= 0 ? 0u : ((1u << lim) - 1u));
-            len += __popc(st.bits[lane][w] & valid);
-        }
+        for (int w = 0; w < nw; w++) len += __popc(st.bits[lane][w]);
         const uint32_t key = (len << 5) | (uint32_t)lane;
         int rank = 0;
 #pragma unroll
@@ -549,30 +573,40 @@ gh_blend_backward_kernel(const uint2* __restrict__ ranges, const uint64_t* __res
     const int py0 = ty * GH_BLOCK_Y + 2 * (blk >> 2);
     const float pxf = (float)px;
 
-    GhBwdPix pix[2];
+    GhBwdPair pr;
+    {
+        float tf[2], bgd[2];
+        uint32_t lastv[2];
 #pragma unroll
-    for (int r = 0; r < 2; r++) {
-        const int py = py0 + r;
-        const bool inside = (px < W) && (py < H);
-        const size_t pi = (size_t)py * W + px;
-        pix[r].pyf = (float)py;
-        pix[r].T_final = inside ? final_T[pi] : 0.f;
-        pix[r].T = pix[r].T_final;
-        pix[r].last = inside ? n_contrib[pi] : 0u;     // pixel blends list positions 1..last
-        pix[r].A = 0.f; pix[r].last_alpha = 0.f; pix[r].last_cdot = 0.f;
-        float bgd = 0.f;
+        for (int r = 0; r < 2; r++) {
+            const int py = py0 + r;
+            const bool inside = (px < W) && (py < H);
+            const size_t pi = (size_t)py * W + px;
+            tf[r] = inside ? final_T[pi] : 0.f;
+            lastv[r] = inside ? n_contrib[pi] : 0u;     // pixel blends list positions 1..last
+            float d[GH_NUM_CHANNELS];
+            bgd[r] = 0.f;
 #pragma unroll
-        for (int ch = 0; ch < GH_NUM_CHANNELS; ch++) {
-            pix[r].dL[ch] = inside ? dL_dpix[ch * plane + pi] : 0.f;
-            bgd += __ldg(bg + ch) * pix[r].dL[ch];
+            for (int ch = 0; ch < GH_NUM_CHANNELS; ch++) {
+                d[ch] = inside ? dL_dpix[ch * plane + pi] : 0.f;
+                bgd[r] += __ldg(bg + ch) * d[ch];
+            }
+#pragma unroll
+            for (int k = 0; k < GH_HALF_C; k++) {
+                if (r == 0) pr.dL0[k] = make_float2(d[2 * k], d[2 * k + 1]);
+                else pr.dL1[k] = make_float2(d[2 * k], d[2 * k + 1]);
+            }
         }
-        pix[r].bg_dot = bgd;
+        pr.T = make_float2(tf[0], tf[1]);
+        pr.ntf_bg = make_float2(-tf[0] * bgd[0], -tf[1] * bgd[1]);
+        pr.npy = make_float2(-(float)py0, -(float)(py0 + 1));
+        pr.A = gh_f2(0.f); pr.last_alpha = gh_f2(0.f); pr.last_cdot = gh_f2(0.f);
+        pr.last0 = lastv[0]; pr.last1 = lastv[1];
     }
     // pixel-coordinate -> NDC chain rule factors (backward.cu:464-465)
     const float ddelx_dx = 0.5f * W, ddely_dy = 0.5f * H;
 
-    const uint32_t glast = s_glast[blk];
-    uint32_t wlast = glast;
+    uint32_t wlast = s_glast[blk];
 #pragma unroll
     for (int o = 4; o < 32; o <<= 1) wlast = max(wlast, __shfl_xor_sync(0xffffffffu, wlast, o));
 
@@ -593,7 +627,7 @@ gh_blend_backward_kernel(const uint2* __restrict__ ranges, const uint64_t* __res
             __syncthreads();
             // per-block lists: each of the 4 warps scan-converts every fourth batch of 32 Gaussians
             for (int word = warp; word * 32 < cnt; word += GH_BWD_THREADS / 32)
-                gh_build_lists_b(st, cnt, word, lane, tx0, ty0);
+                gh_build_lists_b(st, cnt, word, lane, tx0, ty0, base, glast_lane);
             __syncthreads();
         }
         if ((uint32_t)base >= wlast) continue;
@@ -601,13 +635,7 @@ gh_blend_backward_kernel(const uint2* __restrict__ ranges, const uint64_t* __res
         int wi = (cnt + 31) >> 5;
         uint32_t cur = 0;
         while (true) {
-            while (cur == 0 && wi > 0) {
-                wi--;
-                // only list positions < glast can have been blended by a pixel of this block
-                const int lim = (int)glast - (base + wi * 32);
-                const uint32_t valid = lim >= 32 ? 0xffffffffu : (lim <= 0 ? 0u : ((1u << lim) - 1u));
-                cur = st.bits[blk][wi] & valid;
-            }
+            while (cur == 0 && wi > 0) cur = st.bits[blk][--wi];
             const bool act = (cur != 0);
             if (!__any_sync(0xffffffffu, act)) break;
 
@@ -620,9 +648,7 @@ gh_blend_backward_kernel(const uint2* __restrict__ ranges, const uint64_t* __res
             const float2* feat = &st.feat[jj * GH_HALF_C];
             const uint32_t pos = act ? (uint32_t)(base + jj) : 0xffffffffu;
             float v[16];
-            const bool c0 = gh_bwd_pixel<true>(pix[0], g0, g1, feat, pxf, pos, ddelx_dx, ddely_dy, v);
-            const bool c1 = gh_bwd_pixel<false>(pix[1], g0, g1, feat, pxf, pos, ddelx_dx, ddely_dy, v);
-            const bool contrib = c0 | c1;
+            const bool contrib = gh_bwd_pair(pr, g0, g1, feat, pxf, pos, ddelx_dx, ddely_dy, v);
             const uint32_t cm = __ballot_sync(0xffffffffu, contrib);
             if (cm == 0u) continue;
             const float4 s = gh_group4_reduce16(v, lane);

@@ -49,6 +49,8 @@ def main():
     CH = (256, 512, 1024, 4096)
     bsteps = {k: [0, 0] for k in CH}      # backward: [current mapping, sorted mapping]
     fsteps = {k: 0 for k in CH}           # forward: warp = 2 pixel rows, per-pixel lists
+    SHAPES = ((2, 16), (4, 8), (8, 4))
+    fshape = {(k, sh): 0 for k in (256, 512) for sh in SHAPES}
     fpairs = 0
     for t in sample:
         ty, tx = divmod(t, TX)
@@ -93,6 +95,11 @@ def main():
             bsteps[k][1] += int(cb[:, order].view(n, 4, 8).max(2).values.sum())
             cf = torch.nn.functional.pad(fh.int(), (0, 0, 0, n * k - L)).view(n, k, 8, 32).sum(1)   # [chunk, warp, lane]
             fsteps[k] += int(cf.max(2).values.sum())
+            if k in (256, 512):
+                cpix = torch.nn.functional.pad(fh.int(), (0, 0, 0, n * k - L)).view(n, k, 16, 16).sum(1)   # [chunk, y, x]
+                for (hh_, ww_) in SHAPES:
+                    m = cpix.view(n, 16 // hh_, hh_, 16 // ww_, ww_).amax(dim=(2, 4))
+                    fshape[(k, (hh_, ww_))] += int(m.sum())
     print(f"tiles sampled {len(sample)}/{len(occupied)}  R={R}")
     print(f"(pixel,G) contributing pairs      {tot_pix}")
     print(f"(block,G) pairs                   {tot_pairs}   -> pixel efficiency {tot_pix / max(1, tot_pairs * 8):.3f}")
@@ -104,6 +111,8 @@ def main():
               f"sorted {bsteps[k][1]} (eff {tot_pairs / 8 / bsteps[k][1]:.3f})")
     for k in CH:
         print(f"forward  lock-step window {k:5d}: warp steps {fsteps[k]} (lane eff {fpairs / 32 / fsteps[k]:.3f})")
+    for (k, sh), v in fshape.items():
+        print(f"forward window {k} warp shape {sh[0]}x{sh[1]}: warp steps {v} (lane eff {fpairs / 32 / v:.3f})")
 
 
 if __name__ == "__main__":
