@@ -61,6 +61,20 @@ __device__ __forceinline__ void gh_cp_async8(void* smem, const void* gmem) {
 __device__ __forceinline__ void gh_cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::); }
 __device__ __forceinline__ void gh_cp_async_wait_all() { asm volatile("cp.async.wait_group 0;\n" ::: "memory"); }
 
+// Packed FP32 (Blackwell FFMA2 / FMUL2 / FADD2: two IEEE-rounded results per issue slot).  The blend
+// kernels are bound by instruction issue, not by the FP32 pipe, so pairing halves their FP32 cost.
+__device__ __forceinline__ float2 gh_f2(float a) { return make_float2(a, a); }
+__device__ __forceinline__ float2 gh_neg2(float2 a) { return make_float2(-a.x, -a.y); }
+__device__ __forceinline__ float2 gh_mul2(float2 a, float2 b) { return __fmul2_rn(a, b); }
+__device__ __forceinline__ float2 gh_add2(float2 a, float2 b) { return __fadd2_rn(a, b); }
+__device__ __forceinline__ float2 gh_sub2(float2 a, float2 b) { return __fadd2_rn(a, gh_neg2(b)); }
+__device__ __forceinline__ float2 gh_fma2(float2 a, float2 b, float2 c) { return __ffma2_rn(a, b, c); }
+__device__ __forceinline__ float gh_rcp_approx(float x) {
+    float r;
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+    return r;
+}
+
 struct GhStage {
     float4 g0[2][GH_CHUNK];
     float4 g1[2][GH_CHUNK];
@@ -136,20 +150,26 @@ __device__ __forceinline__ void gh_build_pixel_lists(const GhStage& st, uint32_t
         wr0 = min(wr0, __shfl_xor_sync(0xffffffffu, wr0, o));
         wr1 = max(wr1, __shfl_xor_sync(0xffffffffu, wr1, o));
     }
+    // two pixel rows per instruction (FFMA2 / FMUL2 / FADD2); a row without a real span has
+    // disc <= 0 and is masked out below
+    const float2 bbac2 = gh_f2(bbac), aQ2 = gh_f2(aQ), b2 = gh_f2(b), ia2 = gh_f2(ia), gx2 = gh_f2(gx);
+    const float2 off2 = gh_f2(-0.01f), ntx2 = gh_f2(-tx0);
 #pragma unroll
-    for (int r = 0; r < 16; r++) {
-        if (r < wr0 || r > wr1) continue;                           // uniform
-        if (all_pixels) { rowmask[r] = 0xffffu; continue; }
-        const float dy = gy - (ty0 + (float)r);
+    for (int t = 0; t < 8; t++) {
+        if (2 * t + 1 < wr0 || 2 * t > wr1) continue;               // uniform
+        const float2 dy = make_float2(gy - (ty0 + (float)(2 * t)), gy - (ty0 + (float)(2 * t + 1)));
         // a dx^2 + 2 b dy dx + (c dy^2 - Q) <= 0,  dx = gx - px
-        const float disc = fmaf(dy * dy, bbac, aQ);
-        if (disc > 0.f) {
-            const float sq = disc * rsqrtf(disc);
-            const float hb = b * dy;
-            const float lo = (gx + (hb - sq) * ia - 0.01f) - tx0, hi = (gx + (hb + sq) * ia + 0.01f) - tx0;
-            const int p0 = max(0, __float2int_ru(lo)), p1 = min(15, __float2int_rd(hi));
-            if (p0 <= p1) rowmask[r] = ((2u << (p1 - p0)) - 1u) << p0;
-        }
+        const float2 disc = gh_fma2(gh_mul2(dy, dy), bbac2, aQ2);
+        const float2 sq = gh_mul2(disc, make_float2(rsqrtf(disc.x), rsqrtf(disc.y)));
+        const float2 hb = gh_mul2(b2, dy);
+        const float2 lo = gh_add2(gh_add2(gh_fma2(gh_sub2(hb, sq), ia2, gx2), off2), ntx2);
+        const float2 hi = gh_add2(gh_add2(gh_fma2(gh_add2(hb, sq), ia2, gx2), gh_neg2(off2)), ntx2);
+        const int p0a = max(0, __float2int_ru(lo.x)), p1a = min(15, __float2int_rd(hi.x));
+        const int p0b = max(0, __float2int_ru(lo.y)), p1b = min(15, __float2int_rd(hi.y));
+        const uint32_t ma = (disc.x > 0.f && p0a <= p1a) ? (((2u << (p1a - p0a)) - 1u) << p0a) : 0u;
+        const uint32_t mb = (disc.y > 0.f && p0b <= p1b) ? (((2u << (p1b - p0b)) - 1u) << p0b) : 0u;
+        rowmask[2 * t] = all_pixels ? 0xffffu : ma;      // rows outside [r0, r1] have disc <= 0
+        rowmask[2 * t + 1] = all_pixels ? 0xffffu : mb;
     }
 #pragma unroll
     for (int t = 0; t < 8; t++) {
@@ -311,20 +331,6 @@ __device__ __forceinline__ void gh_stage_issue_b(GhStageB& st, int slot, uint32_
     st.id[slot] = id;
 }
 
-// Packed FP32 (Blackwell FFMA2 / FMUL2 / FADD2: two IEEE-rounded results per issue slot).  The blend
-// kernels are bound by instruction issue, not by the FP32 pipe, so pairing halves their FP32 cost.
-__device__ __forceinline__ float2 gh_f2(float a) { return make_float2(a, a); }
-__device__ __forceinline__ float2 gh_neg2(float2 a) { return make_float2(-a.x, -a.y); }
-__device__ __forceinline__ float2 gh_mul2(float2 a, float2 b) { return __fmul2_rn(a, b); }
-__device__ __forceinline__ float2 gh_add2(float2 a, float2 b) { return __fadd2_rn(a, b); }
-__device__ __forceinline__ float2 gh_sub2(float2 a, float2 b) { return __fadd2_rn(a, gh_neg2(b)); }
-__device__ __forceinline__ float2 gh_fma2(float2 a, float2 b, float2 c) { return __ffma2_rn(a, b, c); }
-__device__ __forceinline__ float gh_rcp_approx(float x) {
-    float r;
-    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
-    return r;
-}
-
 // Which of the tile's 32 blocks (4 wide x 2 high; bit = by*4 + bx) can this Gaussian reach with
 // alpha >= 1/255?  Exact-conservative: on each pixel row the set {q(d) <= 2(thr+slack)} is an
 // x-interval obtained from the quadratic; the interval is widened by 0.01 px and rounded outwards to
@@ -382,30 +388,31 @@ __device__ __forceinline__ void gh_build_lists_b(GhStageB& st, int cnt, int word
 // CTA = tile = 4 warps.  A lane owns a vertical pixel pair (x, y0), (x, y0+1); 4 lanes own a 4x2 block;
 // the 8 blocks of a warp walk their own lists in lock-step, i.e. every warp instruction works on EIGHT
 // different Gaussians.  The two pixels of a lane are summed in registers; the 16 gradient components
-// are then reduced over the 4 lanes by a 2-level transposing butterfly (12 shuffles shared by 8
-// Gaussians), leaving four adjacent components per lane = one REDG.E.ADD.F32x4 per lane.
+// are then summed over the 4 lanes through shared memory (gh_group4_reduce16), leaving four adjacent
+// components per lane = one REDG.E.ADD.F32x4 per lane.
 #define GH_BWD_THREADS 128
 
-__device__ __forceinline__ float4 gh_group4_reduce16(const float (&v)[16], int lane) {
-    float w8[8];
-    const bool b1 = lane & 2, b0 = lane & 1;
-#pragma unroll
-    for (int i = 0; i < 8; i += 2) {
-        const float s0 = b1 ? v[i] : v[i + 8], s1 = b1 ? v[i + 1] : v[i + 9];
-        const float k0 = b1 ? v[i + 8] : v[i], k1 = b1 ? v[i + 9] : v[i + 1];
-        const float2 r = gh_add2(make_float2(k0, k1), make_float2(__shfl_xor_sync(0xffffffffu, s0, 2),
-                                                                  __shfl_xor_sync(0xffffffffu, s1, 2)));
-        w8[i] = r.x; w8[i + 1] = r.y;
-    }
-    float2 q[2];
-#pragma unroll
-    for (int i = 0; i < 4; i += 2) {
-        const float s0 = b0 ? w8[i] : w8[i + 4], s1 = b0 ? w8[i + 1] : w8[i + 5];
-        const float k0 = b0 ? w8[i + 4] : w8[i], k1 = b0 ? w8[i + 5] : w8[i + 1];
-        q[i >> 1] = gh_add2(make_float2(k0, k1), make_float2(__shfl_xor_sync(0xffffffffu, s0, 1),
-                                                             __shfl_xor_sync(0xffffffffu, s1, 1)));
-    }
-    return make_float4(q[0].x, q[0].y, q[1].x, q[1].y);   // components 4*(lane&3) + {0,1,2,3}
+// Sum the 16 gradient components over the 4 lanes of a block and leave components 4*(lane&3)+{0..3}
+// in each lane.  Through shared memory: 4 STS.128 + 4 LDS.128 + 6 FADD2 per lane, against 12 SHFL +
+// 24 SEL + 6 FADD2 for a transposing butterfly (the kernel is bound by issue slots).  A lane's record
+// is 80 B (16 floats + pad): the 8 lanes of a quarter-warp store to, and load from, 8 disjoint groups
+// of 4 banks.
+#define GH_RED_STRIDE4 5       // float4 per lane record
+__device__ __forceinline__ float4 gh_group4_reduce16(const float (&v)[16], float4* warp_buf, int lane) {
+    float4* mine = warp_buf + lane * GH_RED_STRIDE4;
+    mine[0] = make_float4(v[0], v[1], v[2], v[3]);
+    mine[1] = make_float4(v[4], v[5], v[6], v[7]);
+    mine[2] = make_float4(v[8], v[9], v[10], v[11]);
+    mine[3] = make_float4(v[12], v[13], v[14], v[15]);
+    __syncwarp();
+    const float4* grp = warp_buf + (lane & 28) * GH_RED_STRIDE4 + (lane & 3);
+    const float4 a = grp[0], b = grp[GH_RED_STRIDE4], c = grp[2 * GH_RED_STRIDE4], d = grp[3 * GH_RED_STRIDE4];
+    __syncwarp();              // the next step overwrites the records
+    const float2 lo = gh_add2(gh_add2(make_float2(a.x, a.y), make_float2(b.x, b.y)),
+                              gh_add2(make_float2(c.x, c.y), make_float2(d.x, d.y)));
+    const float2 hi = gh_add2(gh_add2(make_float2(a.z, a.w), make_float2(b.z, b.w)),
+                              gh_add2(make_float2(c.z, c.w), make_float2(d.z, d.w)));
+    return make_float4(lo.x, lo.y, hi.x, hi.y);
 }
 
 // State of the lane's pixel pair; .x = pixel (x, y0), .y = pixel (x, y0 + 1).
@@ -489,7 +496,9 @@ gh_blend_backward_kernel(const uint2* __restrict__ ranges, const uint64_t* __res
                          const float* __restrict__ dL_dpix,
                          float* __restrict__ acc16)   // [P][16]: colors 0..9, mean2D x,y, conic x,y,w, opacity
 {
-    __shared__ GhStageB st;
+    extern __shared__ __align__(16) unsigned char gh_bwd_smem[];
+    GhStageB& st = *reinterpret_cast<GhStageB*>(gh_bwd_smem);
+    float4* red_buf = reinterpret_cast<float4*>(gh_bwd_smem + sizeof(GhStageB)) + (threadIdx.x >> 5) * 32 * GH_RED_STRIDE4;
     __shared__ uint32_t s_warp_last[GH_BWD_THREADS / 32];
     __shared__ uint32_t s_glast[32];                       // per block: deepest list position any of its pixels blended
     __shared__ uint8_t s_perm[GH_BWD_THREADS / 32][32];    // per warp (redundant copies): rank -> block
@@ -651,7 +660,7 @@ gh_blend_backward_kernel(const uint2* __restrict__ ranges, const uint64_t* __res
             const bool contrib = gh_bwd_pair(pr, g0, g1, feat, pxf, pos, ddelx_dx, ddely_dy, v);
             const uint32_t cm = __ballot_sync(0xffffffffu, contrib);
             if (cm == 0u) continue;
-            const float4 s = gh_group4_reduce16(v, lane);
+            const float4 s = gh_group4_reduce16(v, red_buf, lane);
             if ((cm >> gshift) & 0xfu) {
                 float4* dst = reinterpret_cast<float4*>(acc16 + (size_t)id * 16) + (lane & 3);
                 atomicAdd(dst, s);    // REDG.E.ADD.F32x4
@@ -707,8 +716,10 @@ void gh_launch_blend_backward(int W, int H, int gx, int gy, GhGeomWS geom, GhImg
                               const float* features, const float* bg, const float* dL_dpix,
                               cudaStream_t stream)
 {
+    const int smem = (int)(sizeof(GhStageB) + GH_BWD_THREADS * GH_RED_STRIDE4 * sizeof(float4));
+    cudaFuncSetAttribute(gh_blend_backward_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
     cudaFuncSetAttribute(gh_blend_backward_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
-    gh_blend_backward_kernel<<<gx * gy, GH_BWD_THREADS, 0, stream>>>(img.ranges, bin.inst, geom.geo, features,
+    gh_blend_backward_kernel<<<gx * gy, GH_BWD_THREADS, smem, stream>>>(img.ranges, bin.inst, geom.geo, features,
                                                           W, H, gx, bg, img.final_T, img.n_contrib, dL_dpix,
                                                           geom.acc16);
 }

@@ -52,6 +52,10 @@ def main():
     SHAPES = ((2, 16), (4, 8), (8, 4))
     fshape = {(k, sh): 0 for k in (256, 512) for sh in SHAPES}
     fpairs = 0
+    inst_total = inst_contrib = inst_hit = inst_reached = 0
+    PSHAPES = ((2, 16), (4, 8))            # forward with a vertical pixel pair per lane: warp = row pairs x columns
+    fpair_steps = {(k, sh): 0 for k in (256, 512) for sh in PSHAPES}
+    fpair_entries = 0
     for t in sample:
         ty, tx = divmod(t, TX)
         a, b = int(ranges[t, 0]), int(ranges[t, 1])
@@ -74,6 +78,10 @@ def main():
         pos = torch.arange(L, device=dev)[:, None]
         contributes = hit & (pos < nc.reshape(-1)[None]) & inside.reshape(-1)[None]
         tot_pix += int(contributes.sum())
+        inst_total += L
+        inst_contrib += int(contributes.any(1).sum())
+        inst_hit += int((hit & inside.reshape(-1)[None]).any(1).sum())
+        inst_reached += int(nc.max())
         blk = ((ys // 2) * 4 + (xs // 4)).reshape(-1)                     # [256] -> block id
         bh = torch.stack([hit[:, blk == k].any(1) for k in range(32)], 1)
         glast = torch.stack([nc.reshape(-1)[blk == k].max() for k in range(32)])
@@ -96,11 +104,20 @@ def main():
             cf = torch.nn.functional.pad(fh.int(), (0, 0, 0, n * k - L)).view(n, k, 8, 32).sum(1)   # [chunk, warp, lane]
             fsteps[k] += int(cf.max(2).values.sum())
             if k in (256, 512):
+                ph = fh.view(L, 8, 2, 16).any(2)                                   # [L, row pair, col]: union of the pair
+                if k == 256:
+                    fpair_entries += int(ph.sum())
+                cpp = torch.nn.functional.pad(ph.reshape(L, 128).int(), (0, 0, 0, n * k - L)).view(n, k, 8, 16).sum(1)
+                for (hh_, ww_) in PSHAPES:
+                    m = cpp.view(n, 8 // hh_, hh_, 16 // ww_, ww_).amax(dim=(2, 4))
+                    fpair_steps[(k, (hh_, ww_))] += int(m.sum())
                 cpix = torch.nn.functional.pad(fh.int(), (0, 0, 0, n * k - L)).view(n, k, 16, 16).sum(1)   # [chunk, y, x]
                 for (hh_, ww_) in SHAPES:
                     m = cpix.view(n, 16 // hh_, hh_, 16 // ww_, ww_).amax(dim=(2, 4))
                     fshape[(k, (hh_, ww_))] += int(m.sum())
     print(f"tiles sampled {len(sample)}/{len(occupied)}  R={R}")
+    print(f"instances {inst_total}: before the tile's last contributor {inst_reached}, alpha>=1/255 somewhere in tile {inst_hit}, "
+          f"blended by >=1 pixel {inst_contrib}")
     print(f"(pixel,G) contributing pairs      {tot_pix}")
     print(f"(block,G) pairs                   {tot_pairs}   -> pixel efficiency {tot_pix / max(1, tot_pairs * 8):.3f}")
     print(f"warp steps, current mapping       {tot_cur}   (lane efficiency {tot_pairs / 8 / tot_cur:.3f})")
@@ -111,6 +128,9 @@ def main():
               f"sorted {bsteps[k][1]} (eff {tot_pairs / 8 / bsteps[k][1]:.3f})")
     for k in CH:
         print(f"forward  lock-step window {k:5d}: warp steps {fsteps[k]} (lane eff {fpairs / 32 / fsteps[k]:.3f})")
+    print(f"forward pixel entries {fpairs}; pixel-PAIR entries {fpair_entries} ({fpair_entries / fpairs:.3f} of single)")
+    for (k, sh), v in fpair_steps.items():
+        print(f"forward PAIR window {k} warp {sh[0]} row pairs x {sh[1]} cols: warp steps {v} (lane eff {fpair_entries / 32 / v:.3f})")
     for (k, sh), v in fshape.items():
         print(f"forward window {k} warp shape {sh[0]}x{sh[1]}: warp steps {v} (lane eff {fpairs / 32 / v:.3f})")
 
