@@ -117,18 +117,33 @@ gh_emit_kernel(int P, const int* __restrict__ radii, const GhGeo* __restrict__ g
     int maxcount = count;
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) maxcount = max(maxcount, __shfl_xor_sync(0xffffffffu, maxcount, o));
+    // GH_EMIT_U tiles per round: the slot reservations of a round are independent atomics, so their
+    // L2 round trips overlap instead of adding up
+    constexpr int GH_EMIT_U = 4;
     int x = minx, y = miny;
-    for (int t = 0; t < maxcount; t++) {
-        const bool have = t < count;
-        const int tile = have ? (y * gx + x) : -1;
-        const uint32_t peers = __match_any_sync(0xffffffffu, tile);
-        if (have) {
-            const int leader = __ffs(peers) - 1;
-            uint32_t base = 0;
-            if (lane == leader) base = atomicAdd(&tile_cursor[tile], (uint32_t)__popc(peers));
-            base = __shfl_sync(peers, base, leader);
-            inst[base + __popc(peers & ((1u << lane) - 1u))] = rec;
-            if (++x == maxx) { x = minx; y++; }
+    for (int t0 = 0; t0 < maxcount; t0 += GH_EMIT_U) {
+        int tile[GH_EMIT_U];
+        uint32_t peers[GH_EMIT_U], base[GH_EMIT_U];
+#pragma unroll
+        for (int u = 0; u < GH_EMIT_U; u++) {
+            const bool have = t0 + u < count;
+            tile[u] = have ? (y * gx + x) : -1;
+            if (have && ++x == maxx) { x = minx; y++; }
+        }
+#pragma unroll
+        for (int u = 0; u < GH_EMIT_U; u++) peers[u] = __match_any_sync(0xffffffffu, tile[u]);
+#pragma unroll
+        for (int u = 0; u < GH_EMIT_U; u++) {
+            base[u] = 0;
+            if (tile[u] >= 0 && lane == __ffs(peers[u]) - 1)
+                base[u] = atomicAdd(&tile_cursor[tile[u]], (uint32_t)__popc(peers[u]));
+        }
+#pragma unroll
+        for (int u = 0; u < GH_EMIT_U; u++) {
+            if (tile[u] >= 0) {
+                const uint32_t b = __shfl_sync(peers[u], base[u], __ffs(peers[u]) - 1);
+                inst[b + __popc(peers[u] & ((1u << lane) - 1u))] = rec;
+            }
         }
     }
 }
@@ -211,7 +226,7 @@ gh_segment_sort_kernel(const uint2* __restrict__ seg, const GhCtrl* __restrict__
 {
     __shared__ __align__(16) uint64_t sA[GH_INKERNEL_SORT_MAX];
     __shared__ __align__(16) uint64_t sB[GH_INKERNEL_SORT_MAX];
-    __shared__ uint32_t s_small[3 * 256];
+    __shared__ __align__(16) uint32_t s_small[GH_SORT_SCRATCH_WORDS];
     if (blockIdx.x >= ctrl->nseg) return;
     const uint2 sg = seg[blockIdx.x];
     const uint32_t b0 = sg.x, m = sg.y;

@@ -192,7 +192,7 @@ gh_blend_forward_kernel(const uint2* __restrict__ ranges, uint64_t* inst,
     // a lane only ever touches Gaussians whose alpha >= 1/255 footprint (conservatively) contains
     // its pixel, whatever the other lanes of the warp are doing.
     __shared__ GhStage st;
-    __shared__ uint32_t pixbits[(GH_CHUNK / 32) * 256];   // [word][pixel]
+    __shared__ __align__(16) uint32_t pixbits[(GH_CHUNK / 32) * 256];   // [word][pixel]; also the sort's scratch
 
     const int tile = blockIdx.x;
     const int tx = tile % gx, ty = tile / gx;

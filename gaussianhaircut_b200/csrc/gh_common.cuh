@@ -272,12 +272,14 @@ __device__ __forceinline__ void gh_bitonic_sort(KeyPtr keys, const uint32_t n, c
 // (depth bits, Gaussian index) key.  Sub-buckets that come out long (clustered depths) are sorted
 // by the whole CTA with the bitonic network.  A: records (in/out), B: scratch of the same size,
 // cnt: 3 x 256 words.
+#define GH_SORT_SUB 1024u        // sub-buckets (4 per thread of a 256-thread CTA)
+#define GH_SORT_SCRATCH_WORDS (GH_SORT_SUB + 512u)
 __device__ __forceinline__ void gh_bucket_sort_tile(uint64_t* A, uint64_t* B, uint32_t* cnt, int n, int tid) {
+    // cnt: GH_SORT_SCRATCH_WORDS words of shared scratch (1024 counters / cursors + list of long ranges)
     __shared__ uint32_t s_red[16];
     __shared__ uint32_t s_nbig;
     const int lane = tid & 31, warp = tid >> 5;
-    uint32_t* off = cnt + 256;       // start of each sub-bucket
-    uint32_t* big = cnt + 512;       // list of sub-buckets too long for one thread
+    uint32_t* big = cnt + GH_SORT_SUB;       // (start, length) of thread ranges too long for one thread
     // depth range of the list
     uint32_t dmin = 0xffffffffu, dmax = 0u;
     for (int i = tid; i < n; i += 256) { const uint32_t d = (uint32_t)(A[i] >> 32); dmin = min(dmin, d); dmax = max(dmax, d); }
@@ -287,61 +289,60 @@ __device__ __forceinline__ void gh_bucket_sort_tile(uint64_t* A, uint64_t* B, ui
         dmax = max(dmax, __shfl_xor_sync(0xffffffffu, dmax, o));
     }
     if (lane == 0) { s_red[warp] = dmin; s_red[8 + warp] = dmax; }
-    cnt[tid] = 0u;
+    reinterpret_cast<uint4*>(cnt)[tid] = make_uint4(0u, 0u, 0u, 0u);
     if (tid == 0) s_nbig = 0u;
     __syncthreads();
 #pragma unroll
     for (int w = 0; w < 8; w++) { dmin = min(dmin, s_red[w]); dmax = max(dmax, s_red[8 + w]); }
-    // monotone map depth bits -> sub-bucket 0..255
-    const float inv = 256.0f / ((float)(dmax - dmin) + 1.0f);
+    // monotone map depth bits -> sub-bucket 0..1023
+    const float inv = (float)GH_SORT_SUB / ((float)(dmax - dmin) + 1.0f);
     for (int i = tid; i < n; i += 256) {
         const uint32_t d = (uint32_t)(A[i] >> 32);
-        const uint32_t b = min(255u, (uint32_t)((float)(d - dmin) * inv));
+        const uint32_t b = min(GH_SORT_SUB - 1u, (uint32_t)((float)(d - dmin) * inv));
         atomicAdd(&cnt[b], 1u);
     }
     __syncthreads();
-    {   // exclusive scan of the 256 counts (thread t owns sub-bucket t)
-        const uint32_t c = cnt[tid];
-        uint32_t v = c;
+    int r0, r1;      // this thread's range of B: its 4 consecutive sub-buckets
+    {   // exclusive scan of the counts; thread t owns sub-buckets 4t .. 4t+3
+        const uint4 c = reinterpret_cast<uint4*>(cnt)[tid];
+        const uint32_t sum = c.x + c.y + c.z + c.w;
+        uint32_t v = sum;
 #pragma unroll
         for (int o = 1; o < 32; o <<= 1) { const uint32_t nb = __shfl_up_sync(0xffffffffu, v, o); if (lane >= o) v += nb; }
         if (lane == 31) s_red[warp] = v;
         __syncthreads();
-        uint32_t start = v - c;
+        uint32_t start = v - sum;
 #pragma unroll
         for (int w = 0; w < 8; w++) start += (w < warp) ? s_red[w] : 0u;
-        off[tid] = start;
-        __syncthreads();
-        cnt[tid] = start;            // becomes the scatter cursor
+        r0 = (int)start; r1 = (int)(start + sum);
+        // the counters become scatter cursors
+        reinterpret_cast<uint4*>(cnt)[tid] = make_uint4(start, start + c.x, start + c.x + c.y, start + c.x + c.y + c.z);
     }
     __syncthreads();
     for (int i = tid; i < n; i += 256) {
         const uint64_t key = A[i];
         const uint32_t d = (uint32_t)(key >> 32);
-        const uint32_t b = min(255u, (uint32_t)((float)(d - dmin) * inv));
+        const uint32_t b = min(GH_SORT_SUB - 1u, (uint32_t)((float)(d - dmin) * inv));
         B[atomicAdd(&cnt[b], 1u)] = key;
     }
     __syncthreads();
-    {   // cnt[t] is now the END of sub-bucket t
-        const int b0 = (int)off[tid], b1 = (int)cnt[tid];
-        const int m = b1 - b0;
-        if (m > 24) {
-            big[atomicAdd(&s_nbig, 1u)] = (uint32_t)tid;
-        } else {
-            for (int i = b0 + 1; i < b1; i++) {
-                const uint64_t key = B[i];
-                int j = i - 1;
-                while (j >= b0 && B[j] > key) { B[j + 1] = B[j]; j--; }
-                B[j + 1] = key;
-            }
+    // the range is already partitioned into 4 ordered sub-buckets: insertion sort moves records only
+    // inside their sub-bucket
+    if (r1 - r0 > 32) {
+        const uint32_t q = atomicAdd(&s_nbig, 1u);
+        big[2 * q] = (uint32_t)r0; big[2 * q + 1] = (uint32_t)(r1 - r0);
+    } else {
+        for (int i = r0 + 1; i < r1; i++) {
+            const uint64_t key = B[i];
+            int j = i - 1;
+            while (j >= r0 && B[j] > key) { B[j + 1] = B[j]; j--; }
+            B[j + 1] = key;
         }
     }
     __syncthreads();
     const uint32_t nbig = s_nbig;
-    for (uint32_t q = 0; q < nbig; q++) {
-        const uint32_t t = big[q];
-        gh_bitonic_sort(B + off[t], cnt[t] - off[t], tid, 256);   // ends with a barrier
-    }
+    for (uint32_t q = 0; q < nbig; q++)
+        gh_bitonic_sort(B + big[2 * q], big[2 * q + 1], tid, 256);   // ends with a barrier
     for (int i = tid; i < n; i += 256) A[i] = B[i];
     __syncthreads();
 }

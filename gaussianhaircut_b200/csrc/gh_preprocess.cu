@@ -19,7 +19,7 @@ __device__ __forceinline__ float gh_ndc2pix(float v, int S) {
     return __double2float_rn(t);
 }
 
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(128, 12)
 gh_preprocess_kernel(int P,
                      const float* __restrict__ means3D,
                      const float* __restrict__ scales, float scale_modifier,
@@ -204,7 +204,7 @@ void gh_launch_preprocess(int P, const float* means3D, const float* scales, floa
     const int gx = (W + GH_BLOCK_X - 1) / GH_BLOCK_X, gy = (H + GH_BLOCK_Y - 1) / GH_BLOCK_Y;
     const float focal_y = H / (2.0f * tan_fovy);   // rasterizer_impl.cu:224-225
     const float focal_x = W / (2.0f * tan_fovx);
-    gh_preprocess_kernel<<<(P + 255) / 256, 256, 0, stream>>>(
+    gh_preprocess_kernel<<<(P + 127) / 128, 128, 0, stream>>>(
         P, means3D, scales, scale_modifier, rotations, opacities, cov3D_precomp, conic_precomp,
         viewmatrix, projmatrix, W, H, tan_fovx, tan_fovy, focal_x, focal_y, radii,
         geom.geo, geom.depth, img.tile_count, img.ctrl, gx, gy, prefiltered);

@@ -12,7 +12,7 @@
 
 namespace {
 
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(128, 8)
 gh_preprocess_backward_kernel(int P, const float* __restrict__ means3D, const int* __restrict__ radii,
                               const float* __restrict__ scales, float mod,
                               const float* __restrict__ rotations,
@@ -217,7 +217,7 @@ void gh_launch_preprocess_backward(int P, const float* means3D, const int* radii
     if (conic_precomp != nullptr) return;   // reference: geometry backward is a no-op in this mode (caller unpacks)
     const float focal_y = H / (2.0f * tan_fovy);
     const float focal_x = W / (2.0f * tan_fovx);
-    gh_preprocess_backward_kernel<<<(P + 255) / 256, 256, 0, stream>>>(
+    gh_preprocess_backward_kernel<<<(P + 127) / 128, 128, 0, stream>>>(
         P, means3D, radii, scales, scale_modifier, rotations, cov3D_precomp, viewmatrix, projmatrix,
         focal_x, focal_y, tan_fovx, tan_fovy, acc16, dL_dmean2D, dL_dconic, dL_dopacity, dL_dcolor,
         dL_dmean3D, dL_dcov3D, dL_dscale, dL_drot);
