@@ -435,6 +435,10 @@ def main():
         st = _capi.stage_timing_read()
         lib.gh_stage_timing_enable(0)
         stages = {}
+        if st.get("tile_sort", (0.0, 0))[1] == 0:
+            # every tile list fitted the forward CTA's shared memory: the sort (read + write back of the
+            # 8-byte records) ran inside blend_forward, so its bytes belong to that kernel
+            stage_bytes["blend_forward"] += 8 * last["R"]
         for name, (ms, calls) in st.items():
             if calls == 0:
                 continue

@@ -18,29 +18,48 @@ struct GhAdamGroups {
     int n;
 };
 
-__device__ __forceinline__ int gh_adam_find(const GhAdamGroups& g, unsigned long long i) {
-    int k = 0;
-#pragma unroll
-    for (int j = 0; j < GH_ADAM_MAX_GROUPS; j++) k += (j < g.n - 1 && i >= g.end[j]) ? 1 : 0;
-    return k;
+// MUFU-based square root / reciprocal (about 1 ulp each): the update is bandwidth bound only if the
+// per-element arithmetic stays short.  The result differs from torch's IEEE sqrt + divide by a few
+// ulp of the UPDATE, i.e. ~1e-7 * lr relative to the parameter.
+__device__ __forceinline__ float gh_sqrt_approx(float x) { float r; asm("sqrt.approx.f32 %0, %1;" : "=f"(r) : "f"(x)); return r; }
+__device__ __forceinline__ float gh_rcp_approx(float x) { float r; asm("rcp.approx.f32 %0, %1;" : "=f"(r) : "f"(x)); return r; }
+
+struct GhAdamConst { float beta1, beta2, omb1, omb2, eps, inv_bc2s, step_size; };
+
+__device__ __forceinline__ void gh_adam_elem(float& p, float gr, float& m, float& v, const GhAdamConst& c) {
+    m = fmaf(c.omb1, gr - m, m);                           // exp_avg.lerp_(grad, 1 - beta1)
+    v = fmaf(v, c.beta2, (c.omb2 * gr) * gr);              // mul_(beta2).addcmul_(grad, grad, 1 - beta2)
+    const float denom = fmaf(gh_sqrt_approx(v), c.inv_bc2s, c.eps);   // sqrt(v) / sqrt(bias_correction2) + eps
+    p = fmaf(-(c.step_size * m), gh_rcp_approx(denom), p);            // addcdiv_(exp_avg, denom, -lr / bias_correction1)
 }
 
+// grid = (blocks, groups): blockIdx.y is the parameter group, float4 per thread when the group's four
+// arrays are 16-byte aligned (torch allocations are), scalar tail / fallback otherwise.
 __global__ void __launch_bounds__(256)
-gh_adam_nan_kernel(GhAdamGroups g, unsigned long long total, unsigned int* __restrict__ flag)
+gh_adam_nan_kernel(GhAdamGroups g, unsigned int* __restrict__ flag)
 {
+    const int k = blockIdx.y;
+    const unsigned long long n = g.end[k] - (k ? g.end[k - 1] : 0ull);
+    const float* __restrict__ gr = g.grad[k];
+    const unsigned long long tid = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const unsigned long long nthreads = (unsigned long long)gridDim.x * blockDim.x;
     bool bad = false;
-    for (unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
-         i += (unsigned long long)gridDim.x * blockDim.x) {
-        const int k = gh_adam_find(g, i);
-        const unsigned long long o = i - (k ? g.end[k - 1] : 0ull);
-        const float v = g.grad[k][o];
-        bad |= (v != v);
+    unsigned long long done = 0;
+    if ((reinterpret_cast<size_t>(gr) & 15) == 0) {
+        const unsigned long long n4 = n >> 2;
+        const float4* g4 = reinterpret_cast<const float4*>(gr);
+        for (unsigned long long i = tid; i < n4; i += nthreads) {
+            const float4 x = g4[i];
+            bad |= (x.x != x.x) | (x.y != x.y) | (x.z != x.z) | (x.w != x.w);
+        }
+        done = n4 << 2;
     }
+    for (unsigned long long i = done + tid; i < n; i += nthreads) { const float x = gr[i]; bad |= (x != x); }
     if (__any_sync(0xffffffffu, bad) && (threadIdx.x & 31) == 0) atomicOr(flag, 1u);
 }
 
 __global__ void __launch_bounds__(256)
-gh_adam_update_kernel(GhAdamGroups g, unsigned long long total, float beta1, float beta2, float eps,
+gh_adam_update_kernel(GhAdamGroups g, float beta1, float beta2, float eps,
                       float bc1, float bc2_sqrt, const unsigned int* __restrict__ flag, int* step_state)
 {
     if (flag != nullptr && *flag != 0u) return;     // a gradient held a NaN: skip this step entirely
@@ -50,26 +69,43 @@ gh_adam_update_kernel(GhAdamGroups g, unsigned long long total, float beta1, flo
         bc1 = 1.0f - powf(beta1, (float)step);
         bc2_sqrt = sqrtf(1.0f - powf(beta2, (float)step));
     }
-    for (unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
-         i += (unsigned long long)gridDim.x * blockDim.x) {
-        const int k = gh_adam_find(g, i);
-        const unsigned long long o = i - (k ? g.end[k - 1] : 0ull);
-        const float gr = g.grad[k][o];
-        float m = g.exp_avg[k][o], v = g.exp_avg_sq[k][o];
-        m = m + (1.0f - beta1) * (gr - m);                       // exp_avg.lerp_(grad, 1 - beta1)
-        v = v * beta2 + (1.0f - beta2) * gr * gr;                // mul_(beta2).addcmul_(grad, grad, 1 - beta2)
-        const float denom = sqrtf(v) / bc2_sqrt + eps;
-        const float step_size = g.lr[k] / bc1;
-        g.param[k][o] = g.param[k][o] - step_size * (m / denom); // addcdiv_(exp_avg, denom, -step_size)
-        g.exp_avg[k][o] = m;
-        g.exp_avg_sq[k][o] = v;
+    const int k = blockIdx.y;
+    const unsigned long long n = g.end[k] - (k ? g.end[k - 1] : 0ull);
+    float* __restrict__ P = g.param[k];
+    const float* __restrict__ G = g.grad[k];
+    float* __restrict__ M = g.exp_avg[k];
+    float* __restrict__ V = g.exp_avg_sq[k];
+    GhAdamConst c;
+    c.beta1 = beta1; c.beta2 = beta2; c.omb1 = 1.0f - beta1; c.omb2 = 1.0f - beta2; c.eps = eps;
+    c.inv_bc2s = 1.0f / bc2_sqrt; c.step_size = g.lr[k] / bc1;
+    const unsigned long long tid = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const unsigned long long nthreads = (unsigned long long)gridDim.x * blockDim.x;
+    unsigned long long done = 0;
+    if (((reinterpret_cast<size_t>(P) | reinterpret_cast<size_t>(G) | reinterpret_cast<size_t>(M) | reinterpret_cast<size_t>(V)) & 15) == 0) {
+        const unsigned long long n4 = n >> 2;
+        for (unsigned long long i = tid; i < n4; i += nthreads) {
+            float4 p = reinterpret_cast<float4*>(P)[i];
+            const float4 gr = reinterpret_cast<const float4*>(G)[i];
+            float4 m = reinterpret_cast<float4*>(M)[i], v = reinterpret_cast<float4*>(V)[i];
+            gh_adam_elem(p.x, gr.x, m.x, v.x, c); gh_adam_elem(p.y, gr.y, m.y, v.y, c);
+            gh_adam_elem(p.z, gr.z, m.z, v.z, c); gh_adam_elem(p.w, gr.w, m.w, v.w, c);
+            reinterpret_cast<float4*>(P)[i] = p;
+            reinterpret_cast<float4*>(M)[i] = m;
+            reinterpret_cast<float4*>(V)[i] = v;
+        }
+        done = n4 << 2;
+    }
+    for (unsigned long long i = done + tid; i < n; i += nthreads) {
+        float p = P[i], m = M[i], v = V[i];
+        gh_adam_elem(p, G[i], m, v, c);
+        P[i] = p; M[i] = m; V[i] = v;
     }
     if (step_state != nullptr) {
         // the last CTA to finish advances the counter (every CTA has read it by then)
         __threadfence();
         if (threadIdx.x == 0) {
             const unsigned int t = atomicAdd(reinterpret_cast<unsigned int*>(step_state + 1), 1u);
-            if (t == gridDim.x - 1) { step_state[0] += 1; step_state[1] = 0; }
+            if (t == gridDim.x * gridDim.y - 1) { step_state[0] += 1; step_state[1] = 0; }
         }
     }
 }
@@ -99,11 +135,15 @@ extern "C" int gh_adam_step(int n_groups, float* const* params, const float* con
     if (total == 0) return GH_OK;
     const double bc1 = 1.0 - pow((double)beta1, (double)(step < 1 ? 1 : step));
     const double bc2 = 1.0 - pow((double)beta2, (double)(step < 1 ? 1 : step));
-    const int blocks = (int)((total + 255) / 256 < 148ull * 16 ? (total + 255) / 256 : 148ull * 16);
+    // one grid row per group; enough CTAs per row for the largest group to fill the machine
+    unsigned long long largest = 0;
+    for (int k = 0; k < n_groups; k++) largest = sizes[k] > largest ? sizes[k] : largest;
+    const unsigned long long want = (largest / 4 + 255) / 256;
+    const dim3 grid((unsigned int)(want < 1 ? 1 : (want > 148ull * 8 ? 148ull * 8 : want)), (unsigned int)n_groups);
     if (nan_flag) {
         if (cudaMemsetAsync(nan_flag, 0, sizeof(unsigned int), stream) != cudaSuccess) return GH_E_CUDA;
-        gh_adam_nan_kernel<<<blocks, 256, 0, stream>>>(g, total, nan_flag);
+        gh_adam_nan_kernel<<<grid, 256, 0, stream>>>(g, nan_flag);
     }
-    gh_adam_update_kernel<<<blocks, 256, 0, stream>>>(g, total, beta1, beta2, eps, (float)bc1, (float)sqrt(bc2), nan_flag, step_state);
+    gh_adam_update_kernel<<<grid, 256, 0, stream>>>(g, beta1, beta2, eps, (float)bc1, (float)sqrt(bc2), nan_flag, step_state);
     return cudaGetLastError() == cudaSuccess ? GH_OK : GH_E_CUDA;
 }

@@ -48,7 +48,7 @@ struct GhStageTimer {
         }
     }
     ~GhStageTimer() {
-        if (g_timing) {
+        if (g_timing && g_launches != l0) {      // a stage that launched nothing (in-kernel tile sort) is not a stage
             cudaEventRecord(g_ev1, stream);
             cudaEventSynchronize(g_ev1);
             float ms = 0.f;
