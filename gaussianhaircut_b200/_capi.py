@@ -65,6 +65,8 @@ SIGNATURES = {
         _i, _p]),                            # debug stream
     "gh_mark_visible": (_i, [_i, _p, _p, _p, _p, _p]),
     "gh_adam_step": (_i, [_i, _p, _p, _p, _p, _p, _p, _f, _f, _f, _i, _p, _p, _p]),
+    "gh_image_loss_workspace_size": (_i, [_i, _i, C.POINTER(C.c_size_t)]),
+    "gh_image_loss": (_i, [_i, _i, _p, _p, _p, _p, _p, _f, _f, _f, _f, _p, _p, _p, _p]),
     "gh_debug_export": (_i, [_i, _i, _i, _ll, _p, _p, _p, _p, _p, _p, _p, _p, _p, _p, _p, _p]),
 }
 

@@ -4,6 +4,7 @@
 // reference's NaN guard (SRC/train_gaussians.py:174-181: skip the step if any gradient has a NaN,
 // done there with seven blocking `.isnan().any()` host syncs) is a device-side flag: no host sync.
 #include "gh_common.cuh"
+#include "gh_kernels.h"
 #include "../../include/gh_rasterizer.h"
 
 namespace {
@@ -143,7 +144,9 @@ extern "C" int gh_adam_step(int n_groups, float* const* params, const float* con
     if (nan_flag) {
         if (cudaMemsetAsync(nan_flag, 0, sizeof(unsigned int), stream) != cudaSuccess) return GH_E_CUDA;
         gh_adam_nan_kernel<<<grid, 256, 0, stream>>>(g, nan_flag);
+        gh_count_launches(1);
     }
     gh_adam_update_kernel<<<grid, 256, 0, stream>>>(g, beta1, beta2, eps, (float)bc1, (float)sqrt(bc2), nan_flag, step_state);
+    gh_count_launches(1);
     return cudaGetLastError() == cudaSuccess ? GH_OK : GH_E_CUDA;
 }

@@ -46,3 +46,6 @@ void gh_launch_preprocess_backward(int P, const float* means3D, const int* radii
                                    float* dL_dopacity, float* dL_dcolor,
                                    float* dL_dmean3D, float* dL_dcov3D, float* dL_dscale, float* dL_drot,
                                    cudaStream_t stream);
+
+// kernels launched outside gh_api.cu (optimizer, image losses) report themselves to gh_kernel_launch_count()
+void gh_count_launches(int n);

@@ -185,6 +185,26 @@ int gh_adam_step(int n_groups, float* const* params, const float* const* grads,
                  float beta1, float beta2, float eps, int step, int* step_state,
                  unsigned int* nan_flag, gh_stream_t stream);
 
+/*
+ * "Next" row: the image-space losses of the appearance stage, forward + backward in
+ * one call, consuming the rasterizer's (10,H,W) output and producing dL/dout in the layout gh_backward
+ * reads as dL_dpix.  Replaces, for this step of src/train_gaussians.py:
+ *   l1_loss / ssim / or_loss            src/utils/loss_utils.py:19-48, 73-121
+ *   the dir -> angle post-processing    src/gaussian_renderer/__init__.py:100-105
+ *   the loss composition + NaN guard    src/train_gaussians.py:126-140
+ * out_color (10,H,W): image 0..2, mask 3..4, dir 5..7, orientation confidence 8, depth 9.
+ * gt_image (3,H,W), gt_mask (2,H,W), gt_orient_angle (1,H,W), gt_orient_conf (1,H,W): device float32.
+ * workspace: gh_image_loss_workspace_size bytes, 8-byte aligned.
+ * losses (device float[8]): total, Ll1, Lssim, Lmask, Lorient, sum of orientation weights,
+ *   1 if Lorient was NaN (then it counts as 0 and has no gradient, like the reference), 0.
+ * dL_dout (10,H,W): d total / d out_color, every element written.  No host synchronisation.
+ */
+int gh_image_loss_workspace_size(int width, int height, size_t* bytes);
+int gh_image_loss(int width, int height, const float* out_color, const float* gt_image,
+                  const float* gt_mask, const float* gt_orient_angle, const float* gt_orient_conf,
+                  float lambda_dl1, float lambda_dssim, float lambda_dmask, float lambda_dorient,
+                  void* workspace, float* losses, float* dL_dout, gh_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -5,6 +5,10 @@ Gates (BASELINE.json north_star): tile keys + sort order bit-exact; rendered map
 gradients within 1e-4 relative.  We additionally require radii / per-Gaussian 2-D state /
 final_T / n_contrib to be bit-identical, because every decision of the reference is reproduced.
 """
+import glob
+import os
+import sys
+
 import numpy as np
 import pytest
 import torch
@@ -264,3 +268,66 @@ def test_fused_adam_matches_torch(cuda_device):
         for p, q in zip(p_ref, p_mine):
             assert rel_err(q.detach(), p.detach()) <= 1e-6, f"step {it}"
     assert int(opt_mine.step_state[0]) == 5        # the poisoned step was skipped, like torch's state['step']
+
+
+# ----------------------------------------------------------------------------- 'next' row 4: fused image loss
+LOSS_GOLDEN = sorted(glob.glob(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "loss_*.npz")))
+
+
+def _loss_oracle():
+    sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "oracle"))
+    import loss_oracle
+    return loss_oracle
+
+
+@pytest.mark.parametrize("path", LOSS_GOLDEN, ids=[os.path.basename(p)[:-4] for p in LOSS_GOLDEN])
+def test_image_loss_matches_reference_golden(cuda_device, path):
+    """gh_image_loss against the reference's own loss_utils outputs (CPU autograd), incl. the
+    'sum of weights == 0 -> NaN -> Lorient = 0' guard."""
+    from gaussianhaircut_b200.losses import hair_image_loss
+    lo = _loss_oracle()
+    d = np.load(path)
+    ins = lo.synthetic_case(int(d["W"]), int(d["H"]), int(d["seed"]), device=cuda_device, zero_weights=bool(d["zero_weights"]))
+    render = ins[0].clone().requires_grad_(True)
+    loss, parts = hair_image_loss(render, *ins[1:], *[float(x) for x in d["lambdas"]])
+    loss.backward()
+    assert abs(float(loss.detach()) - float(d["loss"])) <= 1e-5 * abs(float(d["loss"]))
+    for k in ("Ll1", "Lssim", "Lmask", "Lorient"):
+        assert abs(float(parts[k]) - float(d[k])) <= 1e-5 * max(1e-3, abs(float(d[k]))), k
+    assert bool(parts["orient_nan"].item() != 0) == bool(d["zero_weights"])
+    g_ref = torch.from_numpy(d["dL_drender"]).to(cuda_device)
+    for ch in range(10):
+        assert rel_err(render.grad[ch], g_ref[ch]) <= REL_TOL, f"channel {ch}: {rel_err(render.grad[ch], g_ref[ch])}"
+
+
+@pytest.mark.parametrize("W,H", [(1920, 1080), (250, 187)])
+def test_image_loss_matches_oracle_full_size(cuda_device, W, H):
+    """Same check at the benchmark resolution against the PyTorch restatement (oracle/loss_oracle.py) run
+    on the GPU; also a non-unit upstream gradient through the autograd wrapper."""
+    from gaussianhaircut_b200.losses import hair_image_loss
+    lo = _loss_oracle()
+    lambdas = (0.8, 0.2, 0.1, 0.3)
+    ins = lo.synthetic_case(W, H, 7, device=cuda_device)
+    r0 = ins[0].clone().requires_grad_(True)
+    r1 = ins[0].clone().requires_grad_(True)
+    l_ref, p_ref = lo.training_loss(r0, *ins[1:], *lambdas)
+    (l_ref * 3.0).backward()
+    l_mine, p_mine = hair_image_loss(r1, *ins[1:], *lambdas)
+    (l_mine * 3.0).backward()
+    assert abs(float(l_mine.detach()) - float(l_ref.detach())) <= 1e-5 * abs(float(l_ref.detach()))
+    for k in ("Ll1", "Lssim", "Lmask", "Lorient"):
+        assert abs(float(p_mine[k]) - float(p_ref[k])) <= 1e-5 * max(1e-3, abs(float(p_ref[k]))), k
+    for ch in range(10):
+        assert rel_err(r1.grad[ch], r0.grad[ch]) <= REL_TOL, f"channel {ch}: {rel_err(r1.grad[ch], r0.grad[ch])}"
+
+
+def test_image_loss_api_errors(cuda_device):
+    from gaussianhaircut_b200.losses import hair_image_loss
+    lo = _loss_oracle()
+    ins = lo.synthetic_case(32, 24, 0, device=cuda_device)
+    with pytest.raises(RuntimeError):
+        hair_image_loss(ins[0].cpu(), *ins[1:], 1, 1, 1, 1)                 # no CPU path
+    with pytest.raises(RuntimeError):
+        hair_image_loss(ins[0][:9], *ins[1:], 1, 1, 1, 1)                   # not the 10-channel render
+    with pytest.raises(RuntimeError):
+        hair_image_loss(ins[0], ins[1][:, :-1], *ins[2:], 1, 1, 1, 1)       # shape mismatch

@@ -17,7 +17,8 @@ sys.path.insert(0, os.path.join(ROOT, "oracle"))
 import oracle  # noqa: E402
 
 GOLDEN = sorted(glob.glob(os.path.join(ROOT, "tests", "golden", "*_*.npz")))
-GOLDEN = [g for g in GOLDEN if not os.path.basename(g).startswith("pyref")]
+GOLDEN = [g for g in GOLDEN if not os.path.basename(g).startswith(("pyref", "loss_"))]
+LOSS_GOLDEN = sorted(glob.glob(os.path.join(ROOT, "tests", "golden", "loss_*.npz")))
 GRADS = ("dL_dmeans2D", "dL_dcolors", "dL_dopacity", "dL_dmeans3D", "dL_dcov3D", "dL_dconic", "dL_dsh",
          "dL_dscales", "dL_drotations")
 
@@ -133,3 +134,26 @@ def test_oracle_edge_cases():
     assert np.array_equal(fw0["out_color"], np.broadcast_to(bg[:, None, None], (10, H, W)))
     assert np.array_equal(oracle.mark_visible(xyz, vm), np.ones(P, bool))
     assert not oracle.mark_visible(xyz, vm_away).any()
+
+
+@pytest.mark.parametrize("path", LOSS_GOLDEN, ids=[os.path.basename(p)[:-4] for p in LOSS_GOLDEN])
+def test_loss_oracle_matches_reference_loss_utils(path):
+    """'Next' row 4: oracle/loss_oracle.py against outputs of the reference's own loss_utils
+    (tests/golden/make_golden_loss.py), values and autograd gradients."""
+    import torch
+    import loss_oracle
+    d = np.load(path)
+    renders, gt_image, gt_mask, gt_angle, gt_conf = loss_oracle.synthetic_case(int(d["W"]), int(d["H"]), int(d["seed"]),
+                                                                                zero_weights=bool(d["zero_weights"]))
+    renders.requires_grad_(True)
+    loss, parts = loss_oracle.training_loss(renders, gt_image, gt_mask, gt_angle, gt_conf, *[float(x) for x in d["lambdas"]])
+    loss.backward()
+    assert abs(float(loss) - float(d["loss"])) <= 1e-6 * max(1.0, abs(float(d["loss"])))
+    for k in ("Ll1", "Lssim", "Lmask", "Lorient"):
+        assert abs(float(parts[k]) - float(d[k])) <= 1e-6, k
+    g_ref = torch.from_numpy(d["dL_drender"])
+    assert (renders.grad - g_ref).norm() <= 1e-6 * g_ref.norm()
+
+
+def test_loss_golden_present():
+    assert len(LOSS_GOLDEN) >= 3
