@@ -56,6 +56,8 @@ def parse_args():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-roofline", action="store_true")
     ap.add_argument("--ref-steps", type=int, default=10)
+    ap.add_argument("--collective", default="auto", choices=["auto", "peer-mc", "peer-nomc", "nccl"],
+                    help="N>1: gh_allreduce_p2p over symmetric memory (auto: peer ld/st up to 4 GPUs, NVLS multimem from 8) or NCCL")
     return ap.parse_args()
 
 
@@ -206,6 +208,18 @@ def main():
 
     packed = [pack_args(v) for v in views]
     last = {}
+    par = None
+    collective = "none"
+    if use_dist and args.impl == "mine":
+        collective = "nccl all_reduce"
+        if args.collective != "nccl":
+            try:
+                par = ghdist.PeerAllReduce(34 * P, device, use_multicast={"auto": None, "peer-mc": True, "peer-nomc": False}[args.collective])
+                collective = "gh_allreduce_p2p (" + ("NVLS multimem" if par.multicast else "peer loads/stores") + ")"
+            except Exception as exc:      # symmetric memory unavailable on this box: NCCL
+                log(f"[bench] rank {rank}: peer all-reduce unavailable ({exc}); using NCCL")
+                par = None
+        log(f"[bench] rank {rank}: collective = {collective}")
 
     def step(i, mod=native, arena=(args.impl == "mine")):
         fw, kw, s, e, g = packed[i % len(packed)]
@@ -214,11 +228,14 @@ def main():
               g("cov3D_precomp"), g("conic_precomp"), s["viewmatrix"], s["projmatrix"], s["tanfovx"], s["tanfovy"],
               dL, e, s["sh_degree"], s["campos"], geom, R, binning, img, False)
         if arena:
-            flat, grads, _ = mod.rasterize_gaussians_backward_arena(*bw)
+            flat, grads, _ = mod.rasterize_gaussians_backward_arena(*bw, arena_storage=(par.buffer if par is not None else None))
             if use_dist:
                 # one collective per step, over the part of the arena the optimizer reads
-                dist.all_reduce(ghdist.trainable_slice(flat, P, "native" if args.mode == "native" else "any"),
-                                op=dist.ReduceOp.SUM)
+                sl = ghdist.trainable_slice(flat, P, "native" if args.mode == "native" else "any")
+                if par is not None:
+                    par.all_reduce(n_floats=sl.numel())
+                else:
+                    dist.all_reduce(sl, op=dist.ReduceOp.SUM)
             last["grads"] = flat
             last["views"] = grads
         else:
@@ -570,7 +587,7 @@ def main():
             "dtype": "f32", "data": "synthetic",
             "config": {"workload": f"strands({args.strands}) = {P_total} Gaussians, {W}x{H}, fwd+bwd, mode={args.mode}",
                        "gaussians_per_view": P, "num_rendered": int(last["R"]), "views_cycled": args.views,
-                       "parallelism": f"views sharded one per GPU (dp{N}), one NCCL all-reduce of the gradient arena per step" if N > 1 else "single GPU",
+                       "parallelism": f"views sharded one per GPU (dp{N}), one all-reduce of the gradient arena per step: {collective}" if N > 1 else "single GPU",
                        "l2": "per-step footprint ~0.3 GB (83 MB image + 83 MB upstream grad + 68 MB grads + inputs/workspaces) > 126 MB L2; views cycled"},
             "clocks": clocks,
             "e2e": e2e,

@@ -124,11 +124,20 @@ def rasterize_gaussians(
     return R, out_color, radii, geomBuffer, binningBuffer, imgBuffer
 
 
-def alloc_grad_arena(P: int, device: torch.device, zero: bool = True):
+def alloc_grad_arena(P: int, device: torch.device, zero: bool = True, storage: torch.Tensor | None = None):
     """One flat float32 buffer holding all per-Gaussian gradients + named (P, n) views.
-    `zero=False` skips the fill: gh_backward writes every element itself."""
-    alloc = torch.zeros if zero else torch.empty
-    flat = alloc(P * GRAD_FLOATS_PER_GAUSSIAN, dtype=torch.float32, device=device)
+    `zero=False` skips the fill: gh_backward writes every element itself.  `storage`: use (the head of)
+    this float32 buffer instead of allocating, e.g. a symmetric-memory arena (dist.PeerAllReduce)."""
+    n = P * GRAD_FLOATS_PER_GAUSSIAN
+    if storage is not None:
+        if storage.dtype != torch.float32 or storage.numel() < n or not storage.is_contiguous():
+            raise RuntimeError("gradient arena storage must be a contiguous float32 tensor of at least 34 * P elements")
+        flat = storage.view(-1)[:n]
+        if zero:
+            flat.zero_()
+    else:
+        alloc = torch.zeros if zero else torch.empty
+        flat = alloc(n, dtype=torch.float32, device=device)
     views, off = {}, 0
     for name, n in _GRAD_LAYOUT:
         views[name] = flat[off:off + P * n].view(P, n)
@@ -139,17 +148,18 @@ def alloc_grad_arena(P: int, device: torch.device, zero: bool = True):
 def rasterize_gaussians_backward_arena(
     background, means3D, radii, colors, scales, rotations, scale_modifier, cov3D_precomp, conic_precomp,
     viewmatrix, projmatrix, tan_fovx, tan_fovy, dL_dout_color, sh, degree, campos,
-    geomBuffer, R, binningBuffer, imageBuffer, debug,
+    geomBuffer, R, binningBuffer, imageBuffer, debug, arena_storage=None,
 ):
     """Same work as `rasterize_gaussians_backward`, but returns (flat_arena, views, dL_dsh): every
     per-Gaussian gradient is a (P, n) view into ONE flat float32 buffer, which is what a multi-GPU
-    caller all-reduces (one collective per step, no packing copy)."""
+    caller all-reduces (one collective per step, no packing copy).  `arena_storage` places the arena
+    in caller-owned memory (a symmetric-memory buffer for dist.PeerAllReduce)."""
     lib = _capi.load()
     device = means3D.device
     P = int(means3D.size(0))
     H, W = int(dL_dout_color.size(1)), int(dL_dout_color.size(2))
     M = int(sh.size(1)) if sh.numel() != 0 else 0
-    flat, g = alloc_grad_arena(P, device, zero=False)     # gh_backward writes every element
+    flat, g = alloc_grad_arena(P, device, zero=False, storage=arena_storage)     # gh_backward writes every element
     dL_dsh = torch.zeros((P, M, 3), dtype=torch.float32, device=device)
     if P != 0:
         with torch.cuda.device(device):

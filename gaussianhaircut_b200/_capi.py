@@ -66,6 +66,7 @@ SIGNATURES = {
     "gh_mark_visible": (_i, [_i, _p, _p, _p, _p, _p]),
     "gh_adam_step": (_i, [_i, _p, _p, _p, _p, _p, _p, _f, _f, _f, _i, _p, _p, _p]),
     "gh_image_loss_workspace_size": (_i, [_i, _i, C.POINTER(C.c_size_t)]),
+    "gh_allreduce_p2p": (_i, [_p, _p, C.c_ulonglong, _i, _i, C.c_size_t, C.c_size_t, C.c_uint, _p, _p]),
     "gh_image_loss": (_i, [_i, _i, _p, _p, _p, _p, _p, _f, _f, _f, _f, _p, _p, _p, _p]),
     "gh_debug_export": (_i, [_i, _i, _i, _ll, _p, _p, _p, _p, _p, _p, _p, _p, _p, _p, _p, _p]),
 }

@@ -78,3 +78,70 @@ def allreduce_densification_stats(grad_accum: torch.Tensor, denom: torch.Tensor,
     dist.all_reduce(grad_accum, op=dist.ReduceOp.SUM, group=group)
     dist.all_reduce(denom, op=dist.ReduceOp.SUM, group=group)
     dist.all_reduce(max_radii2D, op=dist.ReduceOp.MAX, group=group)
+
+
+class PeerAllReduce:
+    """Sum a float32 gradient arena over the GPUs of one node with `gh_allreduce_p2p`: one kernel per
+    rank that reads and writes the peers' arenas through NVLink (symmetric memory), instead of NCCL.
+
+        par = PeerAllReduce(34 * P, device)                      # once; collective (rendezvous)
+        flat, grads, _ = _C.rasterize_gaussians_backward_arena(..., arena_storage=par.buffer)
+        par.all_reduce(n_floats=24 * P)                          # in place, on the current stream
+        optimizer.step(...)                                      # stream order is enough: no host sync
+
+    `use_multicast`: None = choose by world size (NVLS multimem from 8 GPUs up, when the allocation has a
+    multicast mapping), True / False = force.  Every rank must call `all_reduce` the same number of times
+    with the same range.  `ok()` (host sync)
+    tells whether every peer arrived at every barrier so far."""
+
+    def __init__(self, numel: int, device: torch.device, group: Optional[dist.ProcessGroup] = None,
+                 use_multicast: Optional[bool] = None):
+        import ctypes as C
+        import torch.distributed._symmetric_memory as symm_mem
+        from . import _capi
+        if not dist.is_initialized():
+            raise RuntimeError("PeerAllReduce needs an initialised torch.distributed process group")
+        self.group = group if group is not None else dist.group.WORLD
+        self.world = dist.get_world_size(self.group)
+        self.rank = dist.get_rank(self.group)
+        if self.world > 16:
+            raise RuntimeError("PeerAllReduce supports up to 16 GPUs of one node")
+        self.device = device
+        n = (int(numel) + 3) // 4 * 4
+        with torch.cuda.device(device):
+            self.buffer = symm_mem.empty(n, dtype=torch.float32, device=device)
+            self._flags = symm_mem.empty(64, dtype=torch.int32, device=device)
+            self._flags.zero_()
+            self._local = torch.zeros(4, dtype=torch.int32, device=device)
+            hb = symm_mem.rendezvous(self.buffer, self.group)
+            hf = symm_mem.rendezvous(self._flags, self.group)
+            torch.cuda.synchronize(device)
+        dist.barrier(self.group)                                   # every rank's flag block is zero before anyone signals
+        self._handles = (hb, hf)                                   # keep the mappings alive
+        self._bufs = (C.c_ulonglong * self.world)(*[int(p) for p in hb.buffer_ptrs])
+        self._flagptrs = (C.c_ulonglong * self.world)(*[int(p) for p in hf.buffer_ptrs])
+        mc = int(getattr(hb, "multicast_ptr", 0) or 0)
+        if use_multicast is None:
+            # measured (tools/allreduce_case.py, 48 MB): peer loads/stores win up to 4 GPUs, NVLS multimem at 8
+            use_multicast = self.world >= 8
+        self.multicast = mc if use_multicast else 0
+        self._epoch = 0
+        self._lib = _capi.load()
+        self._capi = _capi
+
+    def all_reduce(self, n_floats: Optional[int] = None, offset_floats: int = 0) -> None:
+        import ctypes as C
+        n = self.buffer.numel() - offset_floats if n_floats is None else int(n_floats)
+        n = (n + 3) // 4 * 4
+        if offset_floats % 4 or offset_floats + n > self.buffer.numel():
+            raise RuntimeError("PeerAllReduce: range must be 4-float aligned and inside the buffer")
+        self._epoch += 1
+        with torch.cuda.device(self.device):
+            stream = C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
+            self._capi.check(self._lib.gh_allreduce_p2p(
+                self._bufs, self._flagptrs, C.c_ulonglong(self.multicast), self.rank, self.world,
+                C.c_size_t(offset_floats), C.c_size_t(n), C.c_uint(self._epoch),
+                C.c_void_p(self._local.data_ptr()), stream))
+
+    def ok(self) -> bool:
+        return int(self._local[2].item()) == 0

@@ -205,6 +205,24 @@ int gh_image_loss(int width, int height, const float* out_color, const float* gt
                   float lambda_dl1, float lambda_dssim, float lambda_dmask, float lambda_dorient,
                   void* workspace, float* losses, float* dL_dout, gh_stream_t stream);
 
+/*
+ * Multi-GPU: sum a float32 buffer that lives in SYMMETRIC memory (the same allocation on
+ * every GPU of the node, each mapped into every process, e.g. torch.distributed._symmetric_memory) over
+ * all ranks, in place, with one kernel per rank that reads and writes its peers' copies through NVLink.
+ * Replaces the NCCL all-reduce of the gradient arena; every rank of the group must make the same call.
+ * peer_bufs / peer_flags: HOST arrays of `world` device addresses (this process's mappings of every
+ *   rank's buffer and of every rank's flag block; flag block = uint32[2 * world], zero-initialised once).
+ * multicast_buf: NVLS multicast mapping of the buffer, or 0 (then plain peer loads/stores are used).
+ * offset_floats, n_floats: the range to reduce (multiples of 4; buffers 16-byte aligned).
+ * epoch: 1, 2, 3, ... strictly increasing per call on every rank.
+ * local_sync: device uint32[4] of this rank, zero-initialised once; word 2 becomes non-zero if a peer
+ *   did not arrive within the (bounded) spin, in which case the result is undefined.
+ */
+int gh_allreduce_p2p(const unsigned long long* peer_bufs, const unsigned long long* peer_flags,
+                     unsigned long long multicast_buf, int rank, int world,
+                     size_t offset_floats, size_t n_floats, unsigned int epoch,
+                     unsigned int* local_sync, gh_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif
