@@ -6,20 +6,24 @@
 // new and built around the shape of strand-aligned Gaussians (long thin ellipses: of the 256 pixels
 // of a tile a splat typically reaches alpha >= 1/255 on ~15):
 //
-//   * a tile (16x16 px) is one CTA of 8 warps; its depth-sorted list is staged in chunks of 256
-//     instances into shared memory with cp.async (LDGSTS), double buffered, indices prefetched two
-//     chunks ahead, so the gather latency overlaps the blending of the previous chunk;
-//   * each staged Gaussian is scan-converted ONCE per tile (one lane per Gaussian) against the tile's
-//     32 blocks of 4x2 pixels: the exact-conservative x-span of {alpha >= 1/255} on every pixel row
-//     gives a 32-bit block mask; 32 warp ballots transpose the masks into one 256-bit list per block;
-//   * a block is owned by 8 lanes (a quarter warp).  The four quarter warps of a warp walk their own
-//     lists in lock-step, i.e. every warp instruction works on FOUR different Gaussians -- lane
-//     utilisation roughly doubles against one-Gaussian-per-warp and a skipped Gaussian costs nothing;
-//   * backward: the 16 gradient components of a Gaussian are reduced over the 8 pixels of a block by
-//     a 3-level transposing butterfly (14 shuffles shared by 4 Gaussians), leaving two adjacent
-//     components per lane, which go out as ONE 64-bit vector reduction (REDG.ADD.F32x2) per lane into
-//     a 64-byte per-Gaussian accumulation record -- instead of 16 scalar atomicAdd per (pixel,
-//     Gaussian) pair in the reference (backward.cu:527,549-558);
+//   forward  (gh_blend_forward_kernel, CTA = tile, 8 warps, one pixel per lane)
+//   * lists of <= 2048 records are depth-sorted by the CTA itself (gh_bucket_sort_tile) before blending;
+//   * the sorted list is staged in chunks of 256 into shared memory with cp.async (LDGSTS), double
+//     buffered, indices prefetched two chunks ahead;
+//   * each staged Gaussian is scan-converted ONCE per tile: the exact-conservative x-span of
+//     {alpha >= 1/255} on every pixel row (two rows per packed-FP32 instruction) gives 16-bit row masks,
+//     a 5-step shuffle transpose turns the 32 (Gaussian) x 32 (pixel) bit matrix into one hit list per
+//     pixel, and every lane walks only ITS pixel's list -- a skipped Gaussian costs nothing;
+//   * the 10 colour channels are accumulated as 5 x (FMUL2 + FFMA2), bit-identical to FMUL + FFMA.
+//   backward (gh_blend_backward_kernel, CTA = tile, 4 warps, a vertical pixel pair per lane)
+//   * one 512-record window staged at a time; Gaussians are scan-converted against the tile's 32 blocks
+//     of 4x2 pixels and a shuffle transpose leaves one bit list per block;
+//   * a block is owned by 4 lanes; the 8 blocks of a warp walk their own lists in lock-step (one warp
+//     instruction works on EIGHT different Gaussians); blocks are assigned to warps by list length;
+//   * the pixel pair is evaluated in packed FP32 (.x upper pixel, .y lower pixel); the 16 gradient
+//     components are summed over the block's 4 lanes through shared memory and leave as ONE
+//     REDG.E.ADD.F32x4 per lane into a 64-byte per-Gaussian record -- instead of 16 scalar atomicAdd
+//     per (pixel, Gaussian) pair in the reference (backward.cu:527,549-558);
 //   * dL/dalpha uses the scalar form of the reference's per-channel suffix recursion
 //     (backward.cu:519-523):  sum_ch (c - accum_rec)[ch] dL[ch]  =  c.dL  -  A,   A' = a_last (c_last.dL) + (1-a_last) A.
 #include "gh_common.cuh"
