@@ -165,7 +165,7 @@ gh_loss_main_kernel(GhLossParams prm, const float* __restrict__ out, const float
     __shared__ float sH4[GH_LH][GH_HS];              // row-filtered x y
     __shared__ double s_part[8];
     const int W = prm.W, H = prm.H;
-    const size_t plane = (size_t)W * H;
+    const int plane = W * H;            // 10 * plane < 2^31 is checked by the host entry point
     const int tx0 = blockIdx.x * GH_LT, ty0 = blockIdx.y * GH_LT;
     const int tid = threadIdx.x;
 
@@ -176,8 +176,8 @@ gh_loss_main_kernel(GhLossParams prm, const float* __restrict__ out, const float
         __syncthreads();
         {   // halo load: warp w takes rows w, w+8, ...; all loads of a thread are issued before the first use
             const int lane = tid & 31, warp = tid >> 5;
-            const float* oc = out + (size_t)c * plane;
-            const float* gc = gt_image + (size_t)c * plane;
+            const float* oc = out + c * plane;
+            const float* gc = gt_image + c * plane;
             const float* mc = gt_mask + plane;
 #pragma unroll
             for (int jb = 0; jb < 6; jb += 3) {
@@ -187,12 +187,12 @@ gh_loss_main_kernel(GhLossParams prm, const float* __restrict__ out, const float
                 const int j = jb + jj;
                 const int hy = warp + 8 * j, gy = ty0 + hy - GH_LR;
                 const bool rowok = hy < GH_LH && gy >= 0 && gy < H;
-                const size_t rowbase = (size_t)(rowok ? gy : 0) * W;
+                const int rowbase = (rowok ? gy : 0) * W;
 #pragma unroll
                 for (int h = 0; h < 2; h++) {
                     const int hx = lane + 32 * h, gx = tx0 + hx - GH_LR;
                     const bool ok = rowok && hx < GH_LH && gx >= 0 && gx < W;
-                    const size_t q = rowbase + (ok ? gx : 0);
+                    const int q = rowbase + (ok ? gx : 0);
                     xo[2 * jj + h] = ok ? oc[q] : 0.f;
                     xg[2 * jj + h] = ok ? gc[q] : 0.f;
                     xm[2 * jj + h] = ok ? mc[q] : 0.f;                 // zero padding (F.conv2d padding=5)
@@ -263,7 +263,7 @@ gh_loss_main_kernel(GhLossParams prm, const float* __restrict__ out, const float
                 const float e12 = e12_4[o];
                 const int py = ty0 + 4 * rg + o;
                 if (px < W && py < H) {
-                    const size_t pi = (size_t)py * W + px;
+                    const int pi = py * W + px;
                     const float mu1 = m.x, mu2 = m.y;
                     const float mu1_sq = mu1 * mu1, mu2_sq = mu2 * mu2, mu12 = mu1 * mu2;
                     const float sg1 = e.x - mu1_sq, sg2 = e.y - mu2_sq, sg12 = e12 - mu12;
@@ -273,7 +273,7 @@ gh_loss_main_kernel(GhLossParams prm, const float* __restrict__ out, const float
                     const float S = a1 * a2 * ib;
                     a_ssim += (double)S;
                     // derivatives of the map w.r.t. conv(x), conv(x^2), conv(x y) at this pixel
-                    float* dm = dmaps + (size_t)c * 3 * plane;
+                    float* dm = dmaps + (size_t)c * 3 * (size_t)plane;
                     dm[pi] = 2.f * mu2 * (a2 - a1) * ib - 2.f * mu1 * S * (b2 - b1) * ib;
                     dm[plane + pi] = -S * __frcp_rn(b2);
                     dm[2 * plane + pi] = 2.f * a1 * ib;
@@ -294,14 +294,14 @@ gh_loss_ssim_bwd_kernel(GhLossParams prm, const float* __restrict__ out, const f
     __shared__ float2 sH01[GH_LH][GH_HS];
     __shared__ float sH2[GH_LH][GH_HS];
     const int W = prm.W, H = prm.H;
-    const size_t plane = (size_t)W * H;
+    const int plane = W * H;            // 10 * plane < 2^31 is checked by the host entry point
     const int tx0 = blockIdx.x * GH_LT, ty0 = blockIdx.y * GH_LT;
     const int tid = threadIdx.x;
     const float n3 = (float)(3.0 * (double)plane);
     const float s_ssim = -prm.l_dssim / n3;       // d loss / d ssim_map(p): Lssim = 1 - mean(map)
     const float s_l1 = prm.l_dl1 / n3;
     for (int c = 0; c < 3; c++) {
-        const float* dm = dmaps + (size_t)c * 3 * plane;
+        const float* dm = dmaps + (size_t)c * 3 * (size_t)plane;
         __syncthreads();
         {   // halo load (map pixels outside the image do not exist: zeros)
             const int lane = tid & 31, warp = tid >> 5;
@@ -313,12 +313,12 @@ gh_loss_ssim_bwd_kernel(GhLossParams prm, const float* __restrict__ out, const f
                 const int j = jb + jj;
                 const int hy = warp + 8 * j, gy = ty0 + hy - GH_LR;
                 const bool rowok = hy < GH_LH && gy >= 0 && gy < H;
-                const size_t rowbase = (size_t)(rowok ? gy : 0) * W;
+                const int rowbase = (rowok ? gy : 0) * W;
 #pragma unroll
                 for (int h = 0; h < 2; h++) {
                     const int hx = lane + 32 * h, gx = tx0 + hx - GH_LR;
                     const bool ok = rowok && hx < GH_LH && gx >= 0 && gx < W;
-                    const size_t q = rowbase + (ok ? gx : 0);
+                    const int q = rowbase + (ok ? gx : 0);
                     x0[2 * jj + h] = ok ? dm[q] : 0.f;
                     x1[2 * jj + h] = ok ? dm[plane + q] : 0.f;
                     x2[2 * jj + h] = ok ? dm[2 * plane + q] : 0.f;
@@ -383,7 +383,7 @@ gh_loss_ssim_bwd_kernel(GhLossParams prm, const float* __restrict__ out, const f
                 const float D2 = D2_4[o];
                 const int py = ty0 + 4 * rg + o;
                 if (px < W && py < H) {
-                    const size_t pi = (size_t)py * W + px;
+                    const int pi = py * W + px;
                     const float m1 = gt_mask[plane + pi];
                     const float I = out[c * plane + pi], G = gt_image[c * plane + pi];
                     const float x = I * m1, y = G * m1;
@@ -439,6 +439,7 @@ extern "C" int gh_image_loss(int width, int height, const float* out_color, cons
         !workspace || !losses || !dL_dout)
         return GH_E_INVALID_ARG;
     if ((size_t)workspace & 7) return GH_E_INVALID_ARG;
+    if ((long long)width * height > (1ll << 27)) return GH_E_INVALID_ARG;      // 32-bit pixel offsets inside the kernels
     GhLossParams prm;
     prm.W = width; prm.H = height;
     prm.l_dl1 = lambda_dl1; prm.l_dssim = lambda_dssim; prm.l_dmask = lambda_dmask; prm.l_dorient = lambda_dorient;
