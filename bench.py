@@ -281,132 +281,6 @@ def main():
     R_mean = float(last["R"])
     log(f"[bench] {args.impl}: {ms_per_step:.3f} ms/step  -> {value / 1e6:.1f} M Gaussians/s  (R={last['R']})")
 
-    # ---------------------------------------------------------------- second figure: + Adam step (BASELINE config 3)
-    with_adam = None
-    if args.mode == "native" and not use_dist:
-        pnames = ("means3D", "scales", "rotations", "colors_precomp", "opacities")
-        gnames = ("means3D", "scales", "rotations", "colors", "opacity")
-        # the op's inputs are activated values (not the trainer's log-/logit-space parameters): keep the
-        # updates negligible so that the workload (R, splat sizes) stays the one being measured
-        lrs = (1e-9, 1e-10, 1e-9, 1e-9, 1e-9)
-        kw0 = packed[0][1]
-        plist = [kw0[n] for n in pnames]
-        if args.impl == "mine":
-            from gaussianhaircut_b200.optim import FusedAdam
-            opt = FusedAdam([{"params": [p], "lr": lr} for p, lr in zip(plist, lrs)], eps=1e-15)
-
-            def adam_step(i):
-                step(0)
-                opt.step(grads=[last["views"][g].reshape(p.shape) for g, p in zip(gnames, plist)])
-        else:
-            for p in plist:
-                p.requires_grad_(True)
-            opt = torch.optim.Adam([{"params": [p], "lr": lr} for p, lr in zip(plist, lrs)], lr=0.0, eps=1e-15)
-            gidx = {"means3D": 3, "scales": 7, "rotations": 8, "colors": 1, "opacity": 2}   # positions in the 9-tuple
-
-            def adam_step(i):
-                step(0)
-                g9 = last["grads"]
-                for gname, p in zip(gnames, plist):
-                    p.grad = g9[gidx[gname]].reshape(p.shape)
-                # the reference trainer's NaN guard: one blocking .isnan().any() per parameter (train_gaussians.py:175-178)
-                for p in plist:
-                    if p.grad is not None and p.grad.isnan().any():
-                        opt.zero_grad(set_to_none=True)
-                opt.step()
-                opt.zero_grad(set_to_none=True)
-        with torch.no_grad():
-            saved = [p.detach().clone() for p in plist]
-            for i in range(3):
-                adam_step(i)
-            ms_adam = timed(args.steps, adam_step)
-            for p, q in zip(plist, saved):
-                p.copy_(q)                                   # restore the scene for the following sections
-        with_adam = {"ms_per_step": ms_adam / args.steps, "value": args.steps * P / (ms_adam * 1e-3), "unit": UNIT,
-                     "optimizer": "gh_adam_step (fused, device-side NaN guard)" if args.impl == "mine"
-                                  else "torch.optim.Adam + per-parameter isnan().any() host syncs (reference trainer)",
-                     "parameters": list(pnames)}
-        log(f"[bench] +Adam: {with_adam['ms_per_step']:.3f} ms/step -> {with_adam['value'] / 1e6:.1f} M Gaussians/s")
-
-    # ---------------------------------------------------------------- third figure: the training iteration built so far
-    # forward -> image-space losses (dL/dout) -> backward -> Adam: the op plus its two neighbours
-    # ('next' rows 4 and 2).  Reference arm: the reference CUDA rasterizer + the PyTorch loss the reference
-    # trainer runs (oracle/loss_oracle.py, a restatement of src/utils/loss_utils.py) through autograd +
-    # torch.optim.Adam with the trainer's NaN host syncs.
-    train_iter = None
-    if args.mode == "native" and not use_dist and with_adam is not None:
-        gen = torch.Generator(device="cpu").manual_seed(11)
-        gt_image = torch.rand(3, H, W, generator=gen).to(device)
-        gt_mask = ((torch.rand(2, H, W, generator=gen) > 0.3).float() * (0.5 + 0.5 * torch.rand(2, H, W, generator=gen))).to(device)
-        gt_angle = torch.rand(1, H, W, generator=gen).to(device)
-        gt_conf = torch.rand(1, H, W, generator=gen).to(device)
-        lambdas = (0.8, 0.2, 0.1, 0.1)      # lambda_dl1, lambda_dssim, lambda_dmask, lambda_dorient
-        fw0, kw0, s0, e0, g0 = packed[0]
-
-        def bw_args(radii, geom, R, binning, img, dLt):
-            return (s0["bg"], kw0["means3D"], radii, g0("colors_precomp"), g0("scales"), g0("rotations"), s0["scale_modifier"],
-                    g0("cov3D_precomp"), g0("conic_precomp"), s0["viewmatrix"], s0["projmatrix"], s0["tanfovx"], s0["tanfovy"],
-                    dLt, e0, s0["sh_degree"], s0["campos"], geom, R, binning, img, False)
-
-        if args.impl == "mine":
-            from gaussianhaircut_b200 import losses as ghl
-            ws = torch.empty(ghl.workspace_elems(W, H), dtype=torch.float64, device=device)
-
-            def loss_only(i):
-                last["loss"] = ghl.image_loss_forward_backward(last["color"], gt_image, gt_mask, gt_angle, gt_conf, *lambdas, workspace=ws)
-
-            def iteration(i):
-                R, color, radii, geom, binning, img = native.rasterize_gaussians(*fw0)
-                losses, dLt = ghl.image_loss_forward_backward(color, gt_image, gt_mask, gt_angle, gt_conf, *lambdas, workspace=ws)
-                flat, grads, _ = native.rasterize_gaussians_backward_arena(*bw_args(radii, geom, R, binning, img, dLt))
-                opt.step(grads=[grads[g].reshape(p.shape) for g, p in zip(gnames, plist)])
-                last["loss"] = losses
-        else:
-            import loss_oracle
-
-            def loss_only(i):
-                c = last["color"].detach().requires_grad_(True)
-                with torch.enable_grad():
-                    l, _ = loss_oracle.training_loss(c, gt_image, gt_mask, gt_angle, gt_conf, *lambdas)
-                    l.backward()
-                last["loss"] = l
-
-            def iteration(i):
-                R, color, radii, geom, binning, img = native.rasterize_gaussians(*fw0)
-                c = color.detach().requires_grad_(True)
-                with torch.enable_grad():
-                    l, _ = loss_oracle.training_loss(c, gt_image, gt_mask, gt_angle, gt_conf, *lambdas)
-                    l.backward()
-                g9 = native.rasterize_gaussians_backward(*bw_args(radii, geom, R, binning, img, c.grad))
-                for gname, p in zip(gnames, plist):
-                    p.grad = g9[gidx[gname]].reshape(p.shape)
-                for p in plist:
-                    if p.grad is not None and p.grad.isnan().any():
-                        opt.zero_grad(set_to_none=True)
-                opt.step()
-                opt.zero_grad(set_to_none=True)
-                last["loss"] = l
-        with torch.no_grad():
-            last["color"] = native.rasterize_gaussians(*fw0)[1]
-            for i in range(3):
-                loss_only(i)
-            ms_loss = timed(args.steps, loss_only) / args.steps
-            saved = [p.detach().clone() for p in plist]
-            for i in range(3):
-                iteration(i)
-            ms_iter = timed(args.steps, iteration) / args.steps
-            for p, q in zip(plist, saved):
-                p.copy_(q)
-        loss_bytes = 100 * W * H      # read render 8 ch + 10 supervision channels... = 60 B/px, write dL 40 B/px
-        train_iter = {"ms_per_step": ms_iter, "value": P / (ms_iter * 1e-3), "unit": UNIT,
-                      "stages": "rasterizer forward -> image losses (L1 + SSIM + mask + orientation, fwd+bwd) -> rasterizer backward -> Adam",
-                      "image_loss_ms": ms_loss,
-                      "image_loss_alg_bytes": loss_bytes,
-                      "image_loss_frac_of_hbm_peak": (loss_bytes / (ms_loss * 1e-3) / 1e9) / measured_peak_gbs()[0],
-                      "image_loss_impl": "gh_image_loss (4 launches)" if args.impl == "mine"
-                                         else "PyTorch restatement of the reference's loss_utils + autograd (oracle/loss_oracle.py)"}
-        log(f"[bench] iteration (fwd + losses + bwd + Adam): {ms_iter:.3f} ms/step; image losses alone {ms_loss:.3f} ms")
-
     # ---------------------------------------------------------------- end to end through the public API
     e2e = None
     if not args.no_e2e:
@@ -574,6 +448,134 @@ def main():
         else:
             cpu_baseline = {"value": None, "unit": UNIT, "cores": sm_count, "kind": "reference",
                             "sample": "oracle/_ref not built on this box"}
+    # (the optimizer / training-iteration figures run LAST so that they cannot perturb the headline sections: the
+    #  reference leg measured 2x slower when it ran after them in the same process)
+    # ---------------------------------------------------------------- second figure: + Adam step (BASELINE config 3)
+    with_adam = None
+    if args.mode == "native" and not use_dist:
+        pnames = ("means3D", "scales", "rotations", "colors_precomp", "opacities")
+        gnames = ("means3D", "scales", "rotations", "colors", "opacity")
+        # the op's inputs are activated values (not the trainer's log-/logit-space parameters): keep the
+        # updates negligible so that the workload (R, splat sizes) stays the one being measured
+        lrs = (1e-9, 1e-10, 1e-9, 1e-9, 1e-9)
+        kw0 = packed[0][1]
+        plist = [kw0[n] for n in pnames]
+        if args.impl == "mine":
+            from gaussianhaircut_b200.optim import FusedAdam
+            opt = FusedAdam([{"params": [p], "lr": lr} for p, lr in zip(plist, lrs)], eps=1e-15)
+
+            def adam_step(i):
+                step(0)
+                opt.step(grads=[last["views"][g].reshape(p.shape) for g, p in zip(gnames, plist)])
+        else:
+            for p in plist:
+                p.requires_grad_(True)
+            opt = torch.optim.Adam([{"params": [p], "lr": lr} for p, lr in zip(plist, lrs)], lr=0.0, eps=1e-15)
+            gidx = {"means3D": 3, "scales": 7, "rotations": 8, "colors": 1, "opacity": 2}   # positions in the 9-tuple
+
+            def adam_step(i):
+                step(0)
+                g9 = last["grads"]
+                for gname, p in zip(gnames, plist):
+                    p.grad = g9[gidx[gname]].reshape(p.shape)
+                # the reference trainer's NaN guard: one blocking .isnan().any() per parameter (train_gaussians.py:175-178)
+                for p in plist:
+                    if p.grad is not None and p.grad.isnan().any():
+                        opt.zero_grad(set_to_none=True)
+                opt.step()
+                opt.zero_grad(set_to_none=True)
+        with torch.no_grad():
+            saved = [p.detach().clone() for p in plist]
+            for i in range(3):
+                adam_step(i)
+            ms_adam = timed(args.steps, adam_step)
+            for p, q in zip(plist, saved):
+                p.copy_(q)                                   # restore the scene for the following sections
+        with_adam = {"ms_per_step": ms_adam / args.steps, "value": args.steps * P / (ms_adam * 1e-3), "unit": UNIT,
+                     "optimizer": "gh_adam_step (fused, device-side NaN guard)" if args.impl == "mine"
+                                  else "torch.optim.Adam + per-parameter isnan().any() host syncs (reference trainer)",
+                     "parameters": list(pnames)}
+        log(f"[bench] +Adam: {with_adam['ms_per_step']:.3f} ms/step -> {with_adam['value'] / 1e6:.1f} M Gaussians/s")
+
+    # ---------------------------------------------------------------- third figure: the training iteration built so far
+    # forward -> image-space losses (dL/dout) -> backward -> Adam: the op plus its two neighbours
+    # ('next' rows 4 and 2).  Reference arm: the reference CUDA rasterizer + the PyTorch loss the reference
+    # trainer runs (oracle/loss_oracle.py, a restatement of src/utils/loss_utils.py) through autograd +
+    # torch.optim.Adam with the trainer's NaN host syncs.
+    train_iter = None
+    if args.mode == "native" and not use_dist and with_adam is not None:
+        gen = torch.Generator(device="cpu").manual_seed(11)
+        gt_image = torch.rand(3, H, W, generator=gen).to(device)
+        gt_mask = ((torch.rand(2, H, W, generator=gen) > 0.3).float() * (0.5 + 0.5 * torch.rand(2, H, W, generator=gen))).to(device)
+        gt_angle = torch.rand(1, H, W, generator=gen).to(device)
+        gt_conf = torch.rand(1, H, W, generator=gen).to(device)
+        lambdas = (0.8, 0.2, 0.1, 0.1)      # lambda_dl1, lambda_dssim, lambda_dmask, lambda_dorient
+        fw0, kw0, s0, e0, g0 = packed[0]
+
+        def bw_args(radii, geom, R, binning, img, dLt):
+            return (s0["bg"], kw0["means3D"], radii, g0("colors_precomp"), g0("scales"), g0("rotations"), s0["scale_modifier"],
+                    g0("cov3D_precomp"), g0("conic_precomp"), s0["viewmatrix"], s0["projmatrix"], s0["tanfovx"], s0["tanfovy"],
+                    dLt, e0, s0["sh_degree"], s0["campos"], geom, R, binning, img, False)
+
+        if args.impl == "mine":
+            from gaussianhaircut_b200 import losses as ghl
+            ws = torch.empty(ghl.workspace_elems(W, H), dtype=torch.float64, device=device)
+
+            def loss_only(i):
+                last["loss"] = ghl.image_loss_forward_backward(last["color"], gt_image, gt_mask, gt_angle, gt_conf, *lambdas, workspace=ws)
+
+            def iteration(i):
+                R, color, radii, geom, binning, img = native.rasterize_gaussians(*fw0)
+                losses, dLt = ghl.image_loss_forward_backward(color, gt_image, gt_mask, gt_angle, gt_conf, *lambdas, workspace=ws)
+                flat, grads, _ = native.rasterize_gaussians_backward_arena(*bw_args(radii, geom, R, binning, img, dLt))
+                opt.step(grads=[grads[g].reshape(p.shape) for g, p in zip(gnames, plist)])
+                last["loss"] = losses
+        else:
+            import loss_oracle
+
+            def loss_only(i):
+                c = last["color"].detach().requires_grad_(True)
+                with torch.enable_grad():
+                    l, _ = loss_oracle.training_loss(c, gt_image, gt_mask, gt_angle, gt_conf, *lambdas)
+                    l.backward()
+                last["loss"] = l
+
+            def iteration(i):
+                R, color, radii, geom, binning, img = native.rasterize_gaussians(*fw0)
+                c = color.detach().requires_grad_(True)
+                with torch.enable_grad():
+                    l, _ = loss_oracle.training_loss(c, gt_image, gt_mask, gt_angle, gt_conf, *lambdas)
+                    l.backward()
+                g9 = native.rasterize_gaussians_backward(*bw_args(radii, geom, R, binning, img, c.grad))
+                for gname, p in zip(gnames, plist):
+                    p.grad = g9[gidx[gname]].reshape(p.shape)
+                for p in plist:
+                    if p.grad is not None and p.grad.isnan().any():
+                        opt.zero_grad(set_to_none=True)
+                opt.step()
+                opt.zero_grad(set_to_none=True)
+                last["loss"] = l
+        with torch.no_grad():
+            last["color"] = native.rasterize_gaussians(*fw0)[1]
+            for i in range(3):
+                loss_only(i)
+            ms_loss = timed(args.steps, loss_only) / args.steps
+            saved = [p.detach().clone() for p in plist]
+            for i in range(3):
+                iteration(i)
+            ms_iter = timed(args.steps, iteration) / args.steps
+            for p, q in zip(plist, saved):
+                p.copy_(q)
+        loss_bytes = 100 * W * H      # read render 8 ch + 10 supervision channels... = 60 B/px, write dL 40 B/px
+        train_iter = {"ms_per_step": ms_iter, "value": P / (ms_iter * 1e-3), "unit": UNIT,
+                      "stages": "rasterizer forward -> image losses (L1 + SSIM + mask + orientation, fwd+bwd) -> rasterizer backward -> Adam",
+                      "image_loss_ms": ms_loss,
+                      "image_loss_alg_bytes": loss_bytes,
+                      "image_loss_frac_of_hbm_peak": (loss_bytes / (ms_loss * 1e-3) / 1e9) / measured_peak_gbs()[0],
+                      "image_loss_impl": "gh_image_loss (4 launches)" if args.impl == "mine"
+                                         else "PyTorch restatement of the reference's loss_utils + autograd (oracle/loss_oracle.py)"}
+        log(f"[bench] iteration (fwd + losses + bwd + Adam): {ms_iter:.3f} ms/step; image losses alone {ms_loss:.3f} ms")
+
     if args.impl == "reference":
         cpu_baseline = {"value": value, "unit": UNIT, "cores": sm_count, "kind": "reference",
                         "sample": f"{args.steps} steps of the same workload; the reference's own CUDA extension "
