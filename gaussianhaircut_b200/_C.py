@@ -20,12 +20,14 @@ NUM_CHANNELS = 10  # reference cuda_rasterizer/config.h:15
 # they are views into ONE flat zero-filled arena so that a multi-GPU caller can all-reduce
 # everything the op produced with a single collective and no packing copy.
 # (rotations first: the native side stores them as one 16-byte vector per Gaussian; conic sits at a
-# multiple of 4 floats per Gaussian for the same reason).  The first 24 floats per Gaussian are the
-# gradients of the op's trainable inputs in the native call shape (scales+rotations, no conic): a
-# multi-GPU caller only has to all-reduce `flat[:P * GRAD_FLOATS_TRAINABLE_NATIVE]`.
-_GRAD_LAYOUT = (("rotations", 4), ("colors", NUM_CHANNELS), ("opacity", 1), ("means2D", 3),
-                ("means3D", 3), ("scales", 3), ("conic", 4), ("cov3D", 6))
-GRAD_FLOATS_TRAINABLE_NATIVE = 4 + NUM_CHANNELS + 1 + 3 + 3 + 3
+# multiple of 4 floats per Gaussian for the same reason).  The first 21 floats per Gaussian are the
+# gradients the optimizer consumes in the native call shape (scales+rotations, no conic): a multi-GPU
+# caller only has to all-reduce `flat[:P * GRAD_FLOATS_TRAINABLE_NATIVE]`.  means2D follows: its gradient
+# is only read for the densification statistics (per-view NORMS are accumulated, so it must not be
+# summed over ranks as a gradient; dist.allreduce_densification_stats reduces the statistics instead).
+_GRAD_LAYOUT = (("rotations", 4), ("colors", NUM_CHANNELS), ("opacity", 1), ("means3D", 3), ("scales", 3),
+                ("means2D", 3), ("conic", 4), ("cov3D", 6))
+GRAD_FLOATS_TRAINABLE_NATIVE = 4 + NUM_CHANNELS + 1 + 3 + 3
 GRAD_FLOATS_PER_GAUSSIAN = sum(n for _, n in _GRAD_LAYOUT)
 
 

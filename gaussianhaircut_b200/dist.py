@@ -37,7 +37,8 @@ def trainable_slice(flat: torch.Tensor, num_gaussians: int, call_shape: str = "n
     """The contiguous prefix of the gradient arena that the optimizer consumes.
 
     `native` (the op computes covariances from scales/rotations): rotations, colors, opacity,
-    means2D, means3D, scales = the first 24 floats per Gaussian; the conic / cov3D segments behind
+    means3D, scales = the first 21 floats per Gaussian; means2D (densification statistics only) and
+    the conic / cov3D segments behind
     it stay zero and need not travel.  Any other call shape: the whole arena.
     """
     from . import _C
@@ -86,7 +87,7 @@ class PeerAllReduce:
 
         par = PeerAllReduce(34 * P, device)                      # once; collective (rendezvous)
         flat, grads, _ = _C.rasterize_gaussians_backward_arena(..., arena_storage=par.buffer)
-        par.all_reduce(n_floats=24 * P)                          # in place, on the current stream
+        par.all_reduce(n_floats=21 * P)                          # in place, on the current stream
         optimizer.step(...)                                      # stream order is enough: no host sync
 
     `use_multicast`: None = choose by world size (NVLS multimem from 8 GPUs up, when the allocation has a

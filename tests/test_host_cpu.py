@@ -139,7 +139,7 @@ def test_grad_arena_layout():
     assert g["rotations"].data_ptr() % 16 == 0          # stored as one float4 per Gaussian
     shapes = {"rotations": 4, "conic": 4, "colors": 10, "cov3D": 6, "means3D": 3, "means2D": 3, "scales": 3, "opacity": 1}
     assert (g["conic"].data_ptr() - flat.data_ptr()) % 16 == 0 and g["rotations"].data_ptr() == flat.data_ptr()
-    assert _C.GRAD_FLOATS_TRAINABLE_NATIVE == 24
+    assert _C.GRAD_FLOATS_TRAINABLE_NATIVE == 21
     assert g["conic"].data_ptr() - flat.data_ptr() == 24 * P * 4
     seen = 0
     for k, n in shapes.items():
