@@ -236,7 +236,7 @@ gh_segment_sort_kernel(const uint2* __restrict__ seg, const GhCtrl* __restrict__
         for (uint32_t i = tid; i < m; i += 256) sA[i] = tmp[b0 + i];
         __syncthreads();
         if (m <= 64) gh_bitonic_sort(sA, m, tid, 256);
-        else gh_bucket_sort_tile(sA, sB, s_small, (int)m, tid);
+        else gh_bucket_sort_tile<256>(sA, sB, s_small, (int)m, tid);
         for (uint32_t i = tid; i < m; i += 256) inst[b0 + i] = sA[i];
     } else {
         gh_bitonic_sort(tmp + b0, m, tid, 256);

@@ -231,7 +231,7 @@ gh_blend_forward_kernel(const uint2* __restrict__ ranges, uint64_t* inst,
         for (int i = tid; i < n; i += 256) skeys[i] = gl[i];
         __syncthreads();
         if (n <= 64) gh_bitonic_sort(skeys, (uint32_t)n, tid, 256);
-        else gh_bucket_sort_tile(skeys, spong, pixbits, n, tid);
+        else gh_bucket_sort_tile<256>(skeys, spong, pixbits, n, tid);
         for (int i = tid; i < n; i += 256) gl[i] = skeys[i];
         __syncthreads();
     }

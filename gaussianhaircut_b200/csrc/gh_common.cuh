@@ -266,46 +266,51 @@ __device__ __forceinline__ void gh_bitonic_sort(KeyPtr keys, const uint32_t n, c
     }
 }
 
-// Sort up to 2048 records held in shared memory with a 256-thread CTA in linear time:
-// one MSD split of the records into 256 sub-buckets by linearly quantised depth (order preserving),
-// then every thread insertion-sorts one sub-bucket (a handful of records) on the full 64-bit
-// (depth bits, Gaussian index) key.  Sub-buckets that come out long (clustered depths) are sorted
-// by the whole CTA with the bitonic network.  A: records (in/out), B: scratch of the same size,
-// cnt: 3 x 256 words.
-#define GH_SORT_SUB 1024u        // sub-buckets (4 per thread of a 256-thread CTA)
+// Sort up to 2048 records held in shared memory with an NT-thread CTA (NT = 128 or 256) in linear time:
+// one MSD split of the records into 1024 sub-buckets by linearly quantised depth (order preserving),
+// then every thread insertion-sorts the records of its 1024 / NT consecutive sub-buckets (the range is
+// already partitioned, so records move only inside their sub-bucket); ranges longer than 32 records
+// fall back to the CTA-wide bitonic network.
+#define GH_SORT_SUB 1024u
 #define GH_SORT_SCRATCH_WORDS (GH_SORT_SUB + 512u)
+template <int NT>
 __device__ __forceinline__ void gh_bucket_sort_tile(uint64_t* A, uint64_t* B, uint32_t* cnt, int n, int tid) {
-    // cnt: GH_SORT_SCRATCH_WORDS words of shared scratch (1024 counters / cursors + list of long ranges)
+    // cnt: GH_SORT_SCRATCH_WORDS words of 16-byte aligned shared scratch (counters / cursors + list of long ranges)
+    constexpr int NW = NT / 32;                    // warps
+    constexpr int V4 = (int)GH_SORT_SUB / 4 / NT;  // uint4 of counters per thread (1 or 2)
     __shared__ uint32_t s_red[16];
     __shared__ uint32_t s_nbig;
     const int lane = tid & 31, warp = tid >> 5;
     uint32_t* big = cnt + GH_SORT_SUB;       // (start, length) of thread ranges too long for one thread
     // depth range of the list
     uint32_t dmin = 0xffffffffu, dmax = 0u;
-    for (int i = tid; i < n; i += 256) { const uint32_t d = (uint32_t)(A[i] >> 32); dmin = min(dmin, d); dmax = max(dmax, d); }
+    for (int i = tid; i < n; i += NT) { const uint32_t d = (uint32_t)(A[i] >> 32); dmin = min(dmin, d); dmax = max(dmax, d); }
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) {
         dmin = min(dmin, __shfl_xor_sync(0xffffffffu, dmin, o));
         dmax = max(dmax, __shfl_xor_sync(0xffffffffu, dmax, o));
     }
     if (lane == 0) { s_red[warp] = dmin; s_red[8 + warp] = dmax; }
-    reinterpret_cast<uint4*>(cnt)[tid] = make_uint4(0u, 0u, 0u, 0u);
+#pragma unroll
+    for (int q = 0; q < V4; q++) reinterpret_cast<uint4*>(cnt)[tid * V4 + q] = make_uint4(0u, 0u, 0u, 0u);
     if (tid == 0) s_nbig = 0u;
     __syncthreads();
 #pragma unroll
-    for (int w = 0; w < 8; w++) { dmin = min(dmin, s_red[w]); dmax = max(dmax, s_red[8 + w]); }
+    for (int w = 0; w < NW; w++) { dmin = min(dmin, s_red[w]); dmax = max(dmax, s_red[8 + w]); }
     // monotone map depth bits -> sub-bucket 0..1023
     const float inv = (float)GH_SORT_SUB / ((float)(dmax - dmin) + 1.0f);
-    for (int i = tid; i < n; i += 256) {
+    for (int i = tid; i < n; i += NT) {
         const uint32_t d = (uint32_t)(A[i] >> 32);
         const uint32_t b = min(GH_SORT_SUB - 1u, (uint32_t)((float)(d - dmin) * inv));
         atomicAdd(&cnt[b], 1u);
     }
     __syncthreads();
-    int r0, r1;      // this thread's range of B: its 4 consecutive sub-buckets
-    {   // exclusive scan of the counts; thread t owns sub-buckets 4t .. 4t+3
-        const uint4 c = reinterpret_cast<uint4*>(cnt)[tid];
-        const uint32_t sum = c.x + c.y + c.z + c.w;
+    int r0, r1;      // this thread's range of B: its 4 * V4 consecutive sub-buckets
+    {   // exclusive scan of the counts
+        uint4 c[V4];
+        uint32_t sum = 0;
+#pragma unroll
+        for (int q = 0; q < V4; q++) { c[q] = reinterpret_cast<uint4*>(cnt)[tid * V4 + q]; sum += c[q].x + c[q].y + c[q].z + c[q].w; }
         uint32_t v = sum;
 #pragma unroll
         for (int o = 1; o < 32; o <<= 1) { const uint32_t nb = __shfl_up_sync(0xffffffffu, v, o); if (lane >= o) v += nb; }
@@ -313,21 +318,25 @@ __device__ __forceinline__ void gh_bucket_sort_tile(uint64_t* A, uint64_t* B, ui
         __syncthreads();
         uint32_t start = v - sum;
 #pragma unroll
-        for (int w = 0; w < 8; w++) start += (w < warp) ? s_red[w] : 0u;
+        for (int w = 0; w < NW; w++) start += (w < warp) ? s_red[w] : 0u;
         r0 = (int)start; r1 = (int)(start + sum);
         // the counters become scatter cursors
-        reinterpret_cast<uint4*>(cnt)[tid] = make_uint4(start, start + c.x, start + c.x + c.y, start + c.x + c.y + c.z);
+        uint32_t run = start;
+#pragma unroll
+        for (int q = 0; q < V4; q++) {
+            const uint4 cur = make_uint4(run, run + c[q].x, run + c[q].x + c[q].y, run + c[q].x + c[q].y + c[q].z);
+            run += c[q].x + c[q].y + c[q].z + c[q].w;
+            reinterpret_cast<uint4*>(cnt)[tid * V4 + q] = cur;
+        }
     }
     __syncthreads();
-    for (int i = tid; i < n; i += 256) {
+    for (int i = tid; i < n; i += NT) {
         const uint64_t key = A[i];
         const uint32_t d = (uint32_t)(key >> 32);
         const uint32_t b = min(GH_SORT_SUB - 1u, (uint32_t)((float)(d - dmin) * inv));
         B[atomicAdd(&cnt[b], 1u)] = key;
     }
     __syncthreads();
-    // the range is already partitioned into 4 ordered sub-buckets: insertion sort moves records only
-    // inside their sub-bucket
     if (r1 - r0 > 32) {
         const uint32_t q = atomicAdd(&s_nbig, 1u);
         big[2 * q] = (uint32_t)r0; big[2 * q + 1] = (uint32_t)(r1 - r0);
@@ -342,8 +351,8 @@ __device__ __forceinline__ void gh_bucket_sort_tile(uint64_t* A, uint64_t* B, ui
     __syncthreads();
     const uint32_t nbig = s_nbig;
     for (uint32_t q = 0; q < nbig; q++)
-        gh_bitonic_sort(B + big[2 * q], big[2 * q + 1], tid, 256);   // ends with a barrier
-    for (int i = tid; i < n; i += 256) A[i] = B[i];
+        gh_bitonic_sort(B + big[2 * q], big[2 * q + 1], tid, NT);   // ends with a barrier
+    for (int i = tid; i < n; i += NT) A[i] = B[i];
     __syncthreads();
 }
 
