@@ -221,8 +221,8 @@ def main():
                 par = None
         log(f"[bench] rank {rank}: collective = {collective}")
 
-    def step(i, mod=native, arena=(args.impl == "mine")):
-        fw, kw, s, e, g = packed[i % len(packed)]
+    def step(i, mod=native, arena=(args.impl == "mine"), plist=None):
+        fw, kw, s, e, g = (plist or packed)[i % len(packed)]
         R, color, radii, geom, binning, img = mod.rasterize_gaussians(*fw)
         bw = (s["bg"], kw["means3D"], radii, g("colors_precomp"), g("scales"), g("rotations"), s["scale_modifier"],
               g("cov3D_precomp"), g("conic_precomp"), s["viewmatrix"], s["projmatrix"], s["tanfovx"], s["tanfovy"],
@@ -280,6 +280,26 @@ def main():
     value = (args.steps * P * n_eff) / (ms_total * 1e-3)
     R_mean = float(last["R"])
     log(f"[bench] {args.impl}: {ms_per_step:.3f} ms/step  -> {value / 1e6:.1f} M Gaussians/s  (R={last['R']})")
+
+    # ---------------------------------------------------------------- the call shapes of the reference trainers (M-call)
+    # render(): cov3D_precomp + conic_precomp; render_hair(): scales/rotations + conic_precomp
+    call_shapes = None
+    if args.mode == "native" and not use_dist:
+        call_shapes = {}
+        for m in ("render", "render_hair"):
+            vm = []
+            for v in range(args.views):
+                cam = synth.make_camera((v * 8) % 64, W, H)
+                vm.append(pack_args(synth.rasterizer_inputs(scene, cam, mode=m, device=device)))
+            P_m = vm[0][1]["means3D"].shape[0]
+            fn = (lambda i, vm=vm: step(i, arena=False, plist=vm)) if args.impl == "mine" else (lambda i, vm=vm: step(i, mod=native, arena=False, plist=vm))
+            for i in range(max(3, len(vm))):
+                fn(i)
+            ms_m = timed(args.steps, fn) / args.steps
+            call_shapes[m] = {"ms_per_step": ms_m, "value": P_m / (ms_m * 1e-3), "unit": UNIT, "gaussians_per_view": int(P_m)}
+            log(f"[bench] call shape {m}: {ms_m:.3f} ms/step -> {P_m / ms_m / 1e3:.1f} M Gaussians/s (P={P_m})")
+            del vm
+        last["R"] = int(R_mean)
 
     # ---------------------------------------------------------------- end to end through the public API
     e2e = None
@@ -598,6 +618,7 @@ def main():
             "path_roofline": {"alg_bytes": int(path_bytes), "achieved": path_gbs, "peak": peak, "unit": "GB/s",
                               "frac": path_gbs / peak, "formula": "400P+52R+96WH+24T (344P if conic supplied)"},
             "stages": stages,
+            "call_shapes": call_shapes,
             "with_adam": with_adam,
             "train_iteration": train_iter,
             "cpu_baseline": cpu_baseline,
