@@ -225,11 +225,39 @@ gh_blend_forward_kernel(const uint2* __restrict__ ranges, uint64_t* inst,
     // one kernel the two overlap across the CTAs of an SM.  The sorted bucket is written back for the
     // backward pass.  Longer lists were sorted by gh_tile_sort_kernel before this launch.
     if (n >= 2 && n <= (int)GH_INKERNEL_SORT_MAX) {
-        uint64_t* skeys = reinterpret_cast<uint64_t*>(&st.g0[0][0]);     // g0 + g1 = 16 KB contiguous
+        uint64_t* sbase = reinterpret_cast<uint64_t*>(&st.g0[0][0]);     // g0 + g1 = 16 KB contiguous
         uint64_t* spong = reinterpret_cast<uint64_t*>(&st.feat[0][0]);   // next 16 KB (feat is 20 KB)
         uint64_t* gl = inst + rg.x;
-        for (int i = tid; i < n; i += 256) skeys[i] = gl[i];
-        __syncthreads();
+        // The bucket is one contiguous run of 8-byte records: the TMA engine copies it into shared memory
+        // (cp.async.bulk, one request, completion on an mbarrier) instead of a load/store loop.  Bulk copies
+        // move 16-byte granules, so the run is widened to even record indices; `skeys` skips the extra
+        // leading record.  The rare run that would not fit after widening takes the loop.
+        const uint32_t odd = rg.x & 1u;
+        const uint32_t nrec = ((uint32_t)n + odd + 1u) & ~1u;
+        uint64_t* skeys = sbase + odd;
+        if (nrec <= GH_INKERNEL_SORT_MAX) {
+            __shared__ __align__(8) uint64_t s_mbar;
+            const uint32_t mbar = (uint32_t)__cvta_generic_to_shared(&s_mbar);
+            if (tid == 0) {
+                asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(mbar) : "memory");
+                asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+            }
+            __syncthreads();
+            if (tid == 0) {
+                const uint32_t bytes = nrec * 8u;
+                asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(mbar), "r"(bytes) : "memory");
+                asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                             ::"r"((uint32_t)__cvta_generic_to_shared(sbase)), "l"(gl - odd), "r"(bytes), "r"(mbar) : "memory");
+            }
+            uint32_t landed = 0;
+            for (uint32_t it = 0; it < (1u << 24) && !landed; it++)
+                asm volatile("{\n .reg .pred p;\n mbarrier.try_wait.parity.shared::cta.b64 p, [%1], 0;\n selp.u32 %0, 1, 0, p;\n}"
+                             : "=r"(landed) : "r"(mbar) : "memory");
+            if (!landed) __trap();            // the copy engine never reported completion
+        } else {
+            for (int i = tid; i < n; i += 256) skeys[i] = gl[i];
+            __syncthreads();
+        }
         if (n <= 64) gh_bitonic_sort(skeys, (uint32_t)n, tid, 256);
         else gh_bucket_sort_tile<256>(skeys, spong, pixbits, n, tid);
         for (int i = tid; i < n; i += 256) gl[i] = skeys[i];
