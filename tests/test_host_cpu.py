@@ -230,3 +230,36 @@ def test_arena_allreduce_gloo_world2(tmp_path):
     outs = [p.communicate(timeout=120) for p in procs]
     for r, (p, (o, e)) in enumerate(zip(procs, outs)):
         assert p.returncode == 0 and f"RANK_OK {r}" in o, e[-2000:]
+
+
+def test_image_loss_has_no_cpu_path():
+    """'Next' row 4: the fused image loss fails loudly on CPU tensors (no fallback), and validates shapes."""
+    from gaussianhaircut_b200.losses import hair_image_loss
+    H, W = 8, 12
+    args = (torch.zeros(10, H, W), torch.zeros(3, H, W), torch.zeros(2, H, W), torch.zeros(1, H, W), torch.zeros(1, H, W))
+    with pytest.raises(RuntimeError, match="no CPU path"):
+        hair_image_loss(*args, 1.0, 1.0, 1.0, 1.0)
+    with pytest.raises(RuntimeError, match=r"\(10, H, W\)"):
+        hair_image_loss(torch.zeros(9, H, W), *args[1:], 1.0, 1.0, 1.0, 1.0)
+
+
+def test_trainable_slice_and_peer_allreduce_guards():
+    from gaussianhaircut_b200 import _C, dist as gd
+    P = 12
+    flat, g = _C.alloc_grad_arena(P, torch.device("cpu"))
+    sl = gd.trainable_slice(flat, P, "native")
+    assert sl.numel() == 21 * P and sl.data_ptr() == flat.data_ptr()
+    # the prefix is exactly rotations | colors | opacity | means3D | scales
+    for k in ("rotations", "colors", "opacity", "means3D", "scales"):
+        assert flat.data_ptr() <= g[k].data_ptr() < flat.data_ptr() + 21 * P * 4
+    for k in ("means2D", "conic", "cov3D"):
+        assert g[k].data_ptr() >= flat.data_ptr() + 21 * P * 4
+    assert gd.trainable_slice(flat, P, "render").numel() == flat.numel()
+    with pytest.raises(RuntimeError, match="process group"):
+        gd.PeerAllReduce(34 * P, torch.device("cpu"))
+    # caller-owned arena storage
+    store = torch.zeros(34 * P + 5)
+    flat2, g2 = _C.alloc_grad_arena(P, torch.device("cpu"), zero=False, storage=store)
+    assert flat2.data_ptr() == store.data_ptr() and flat2.numel() == 34 * P
+    with pytest.raises(RuntimeError):
+        _C.alloc_grad_arena(P, torch.device("cpu"), storage=torch.zeros(10))
