@@ -234,8 +234,9 @@ gh_blend_forward_kernel(const uint2* __restrict__ ranges, uint64_t* inst,
         // leading record.  The rare run that would not fit after widening takes the loop.
         const uint32_t odd = rg.x & 1u;
         const uint32_t nrec = ((uint32_t)n + odd + 1u) & ~1u;
-        uint64_t* skeys = sbase + odd;
+        uint64_t* skeys = sbase;                  // the loop path below uses the whole 2048-record buffer
         if (nrec <= GH_INKERNEL_SORT_MAX) {
+            skeys = sbase + odd;
             __shared__ __align__(8) uint64_t s_mbar;
             const uint32_t mbar = (uint32_t)__cvta_generic_to_shared(&s_mbar);
             if (tid == 0) {

@@ -140,6 +140,41 @@ def test_long_tile_lists(cuda_device):
     _check_grads(o)
 
 
+def _two_tile_scene(n_first, n_second, W=32, H=16):
+    """n_first tiny splats in the middle of tile 0 and n_second in the middle of tile 1 (camera 0), distinct
+    depths: bucket 1 starts at record n_first and holds exactly n_second records."""
+    synth = _util.synth
+    P = n_first + n_second
+    f = 1.2 * H
+    px = torch.cat([torch.full((n_first,), 8.0), torch.full((n_second,), 24.0)]).double()
+    py = torch.full((P,), 8.0).double()
+    z = 0.5 + 1e-4 * torch.arange(P).flip(0).double()          # unsorted on purpose (descending depth)
+    x_cam = z * (2 * px + 1 - W) / (2 * f)
+    y_cam = z * (2 * py + 1 - H) / (2 * f)
+    xyz = torch.stack([-x_cam, y_cam, 0.8 - z], 1).float()      # camera 0: x_cam = -x_w, y_cam = y_w, z_cam = 0.8 - z_w
+    scene = synth.make_blob_scene(P, seed=11)
+    scene["xyz"] = xyz
+    scene["scaling"] = torch.full((P, 3), 1e-4)
+    scene["rotation"] = torch.tensor([[1.0, 0.0, 0.0, 0.0]]).repeat(P, 1)
+    scene["opacity"] = torch.full((P, 1), 0.02)                # low alpha: the whole list is blended
+    return scene, synth.make_camera(0, W, H)
+
+
+@pytest.mark.parametrize("n_first,n_second", [(1, 2048), (1, 2047), (2, 2048), (1, 2046), (3, 2049)])
+def test_in_cta_sort_boundary(cuda_device, n_first, n_second):
+    """Buckets of 2046..2049 records starting at odd / even record indices: the widened TMA load of the
+    bucket, its fallback loop (bucket would not fit after widening) and the hand-over to the long-list
+    kernels at 2049 -- sort order and everything downstream against the reference build."""
+    scene, cam = _two_tile_scene(n_first, n_second)
+    inp = _util.synth.rasterizer_inputs(scene, cam, mode="native", device=cuda_device)
+    o = _run_both(inp, cuda_device)
+    rg = o["mine_state"]["ranges"].view(np.uint32)
+    assert int(rg[0, 1] - rg[0, 0]) == n_first and int(rg[1, 0]) == n_first and int(rg[1, 1] - rg[1, 0]) == n_second
+    _check_binning(o)
+    _check_image(o)
+    _check_grads(o)
+
+
 def test_nothing_visible(cuda_device):
     """R == 0: every pixel is the background (rasterizer_impl.cu:287-289, forward.cu:393-399)."""
     import gaussianhaircut_b200._C as mine
