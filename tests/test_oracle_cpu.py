@@ -112,6 +112,38 @@ def test_synth_preamble_matches_reference_python():
     assert torch.equal(synth.filter_points(pre, scene, cam), torch.from_numpy(d["points_mask"]))
 
 
+def test_synth_preamble_gradients_match_reference_python():
+    """Groundwork for SURVEY 8f row 1 (fused projection preamble): the restated preamble's autograd gradients
+    -- w.r.t. the Gaussian parameters AND the camera matrices -- against the reference's own PyTorch stage 1
+    differentiated on the CPU (tests/golden/make_golden_pyref_grad.py)."""
+    import torch
+    import torch.nn.functional as F
+    from gaussianhaircut_b200 import synth
+    d = np.load(os.path.join(ROOT, "tests", "golden", "pyref_stage1_grad.npz"))
+    scene = synth.make_strand_scene(int(d["strands"]), seed=int(d["seed"]))
+    cam = dict(synth.make_camera(int(d["cam_k"]), int(d["W"]), int(d["H"])))
+    leaf = lambda t: t.clone().requires_grad_(True)   # noqa: E731
+    xyz, log_s, rot = leaf(scene["xyz"]), leaf(torch.log(scene["scaling"])), leaf(scene["rotation"])
+    f_dc, f_rest = leaf(scene["f_dc"]), leaf(scene["f_rest"])
+    vm, pm, cc = leaf(cam["world_view_transform"]), leaf(cam["full_proj_transform"]), leaf(cam["camera_center"])
+    cam.update(world_view_transform=vm, full_proj_transform=pm, camera_center=cc)
+    sc = dict(scene, xyz=xyz, scaling=torch.exp(log_s), rotation=F.normalize(rot, dim=-1), f_dc=f_dc, f_rest=f_rest)
+    pre = synth.caller_preamble(sc, cam)
+    dirs = xyz - cc[None]
+    dirs = dirs / dirs.norm(dim=1, keepdim=True)
+    rgb = synth.eval_sh(3, torch.cat([f_dc, f_rest], dim=1).transpose(1, 2), dirs)
+    g = torch.Generator().manual_seed(int(d["weight_seed"]))
+    Wc, Wm, Wd, Wr = (torch.rand(t.shape, generator=g) for t in (pre["conic"], pre["means2D"], pre["depths"], rgb))
+    loss = (pre["conic"] * Wc).sum() * 1e-3 + (pre["means2D"] * Wm).sum() + (pre["depths"] * Wd).sum() + (rgb * Wr).sum()
+    loss.backward()
+    assert abs(float(loss.detach()) - float(d["loss"])) <= 2e-4 * abs(float(d["loss"]))
+    for name, t in (("g_xyz", xyz), ("g_log_scaling", log_s), ("g_rotation", rot), ("g_f_dc", f_dc), ("g_f_rest", f_rest),
+                    ("g_viewmatrix", vm), ("g_projmatrix", pm), ("g_campos", cc)):
+        ref = torch.from_numpy(d[name])
+        err = (t.grad - ref).norm().item() / max(ref.norm().item(), 1e-30)
+        assert err <= 5e-4, f"{name}: relative error {err}"
+
+
 def test_oracle_edge_cases():
     """R == 0 -> pure background; zero-determinant conic dropped; W,H not multiples of 16."""
     rng = np.random.default_rng(0)
