@@ -162,10 +162,10 @@ def main():
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         dist.init_process_group("nccl", device_id=device)
 
-    from gaussianhaircut_b200 import synth
     from gaussianhaircut_b200 import dist as ghdist
     sys.path.insert(0, os.path.join(ROOT, "oracle"))
     import build_ref
+    import synth          # seeded scene / camera generator (test infrastructure, oracle/synth.py)
 
     if args.impl == "mine":
         import gaussianhaircut_b200._C as native
@@ -210,16 +210,56 @@ def main():
     last = {}
     par = None
     collective = "none"
+    allreduce_check = None
     if use_dist and args.impl == "mine":
         collective = "nccl all_reduce"
+        n_arena, n_train = native.arena_floats(P), native.trainable_floats(P)
         if args.collective != "nccl":
             try:
-                par = ghdist.PeerAllReduce(34 * P, device, use_multicast={"auto": None, "peer-mc": True, "peer-nomc": False}[args.collective])
+                par = ghdist.PeerAllReduce(n_arena, device, use_multicast={"auto": None, "peer-mc": True, "peer-nomc": False}[args.collective])
                 collective = "gh_allreduce_p2p (" + ("NVLS multimem" if par.multicast else "peer loads/stores") + ")"
             except Exception as exc:      # symmetric memory unavailable on this box: NCCL
                 log(f"[bench] rank {rank}: peer all-reduce unavailable ({exc}); using NCCL")
                 par = None
         log(f"[bench] rank {rank}: collective = {collective}")
+        if par is not None:
+            # correctness of the hand-written collective where the driver runs it: both data paths against
+            # NCCL on the same arena contents, bit-identical across ranks; any mismatch aborts the bench
+            def check_path(p_obj, label):
+                g = torch.Generator(device="cpu").manual_seed(4242 + rank)
+                for rnd, nfl in enumerate((n_train, n_arena)):
+                    x = (torch.randn(n_arena, generator=g) * (10.0 ** (rnd - 1))).to(device)
+                    p_obj.buffer[:n_arena].copy_(x)
+                    ref = x.clone()
+                    dist.all_reduce(ref[:nfl], op=dist.ReduceOp.SUM)
+                    p_obj.all_reduce(n_floats=nfl)
+                    torch.cuda.synchronize(device)
+                    if not p_obj.ok():
+                        raise SystemExit(f"[bench] rank {rank}: gh_allreduce_p2p ({label}): a peer did not arrive")
+                    err = float((p_obj.buffer[:n_arena] - ref).abs().max() / ref.abs().max().clamp_min(1e-30))
+                    if not err <= 1e-6:
+                        raise SystemExit(f"[bench] rank {rank}: gh_allreduce_p2p ({label}) differs from NCCL all_reduce: rel err {err}")
+                    if nfl < n_arena and not torch.equal(p_obj.buffer[nfl:n_arena], x[nfl:]):
+                        raise SystemExit(f"[bench] rank {rank}: gh_allreduce_p2p ({label}) touched floats outside the requested range")
+                    digest = p_obj.buffer[:n_arena].view(torch.int32).to(torch.int64).sum().reshape(1)
+                    every = [torch.zeros_like(digest) for _ in range(N)]
+                    dist.all_gather(every, digest)
+                    if any(int(t) != int(every[0]) for t in every):
+                        raise SystemExit(f"[bench] gh_allreduce_p2p ({label}): ranks hold different sums")
+                    if int(p_obj.nan_flag.item()) != 0:
+                        raise SystemExit(f"[bench] gh_allreduce_p2p ({label}): spurious NaN flag")
+                return label
+
+            checked = [check_path(par, "NVLS multimem" if par.multicast else "peer loads/stores")]
+            try:
+                other = ghdist.PeerAllReduce(n_arena, device, use_multicast=not bool(par.multicast))
+                if bool(other.multicast) != bool(par.multicast):
+                    checked.append(check_path(other, "NVLS multimem" if other.multicast else "peer loads/stores"))
+                del other
+            except Exception as exc:
+                log(f"[bench] rank {rank}: second data path not checked ({exc})")
+            allreduce_check = "ok (" + ", ".join(checked) + " == NCCL all_reduce <= 1e-6, bit-identical across ranks)"
+            log(f"[bench] rank {rank}: allreduce_check = {allreduce_check}")
 
     def step(i, mod=native, arena=(args.impl == "mine"), plist=None):
         fw, kw, s, e, g = (plist or packed)[i % len(packed)]
@@ -614,6 +654,7 @@ def main():
             "clocks": clocks,
             "e2e": e2e,
             "gpu_launches": gpu_launches,
+            "allreduce_check": allreduce_check,
             "roofline": roofline,
             "path_roofline": {"alg_bytes": int(path_bytes), "achieved": path_gbs, "peak": peak, "unit": "GB/s",
                               "frac": path_gbs / peak, "formula": "400P+52R+96WH+24T (344P if conic supplied)"},

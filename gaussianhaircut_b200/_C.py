@@ -27,8 +27,25 @@ NUM_CHANNELS = 10  # reference cuda_rasterizer/config.h:15
 # summed over ranks as a gradient; dist.allreduce_densification_stats reduces the statistics instead).
 _GRAD_LAYOUT = (("rotations", 4), ("colors", NUM_CHANNELS), ("opacity", 1), ("means3D", 3), ("scales", 3),
                 ("means2D", 3), ("conic", 4), ("cov3D", 6))
+_N_TRAINABLE_SEGMENTS = 5
 GRAD_FLOATS_TRAINABLE_NATIVE = 4 + NUM_CHANNELS + 1 + 3 + 3
 GRAD_FLOATS_PER_GAUSSIAN = sum(n for _, n in _GRAD_LAYOUT)
+
+
+def _seg_floats(P: int, n: int) -> int:
+    """Every arena segment is padded to a multiple of 4 floats: segments stay 16-byte aligned for any P and
+    a 4-float-granular all-reduce of the trainable prefix never touches the means2D segment behind it."""
+    return (P * n + 3) // 4 * 4
+
+
+def arena_floats(P: int) -> int:
+    """float32 elements of the gradient arena for P Gaussians (34 * P when P % 4 == 0)."""
+    return sum(_seg_floats(P, n) for _, n in _GRAD_LAYOUT)
+
+
+def trainable_floats(P: int) -> int:
+    """Length of the arena prefix the optimizer consumes in the native call shape (21 * P when P % 4 == 0)."""
+    return sum(_seg_floats(P, n) for _, n in _GRAD_LAYOUT[:_N_TRAINABLE_SEGMENTS])
 
 
 def _ptr(t: Optional[torch.Tensor]):
@@ -130,10 +147,10 @@ def alloc_grad_arena(P: int, device: torch.device, zero: bool = True, storage: t
     """One flat float32 buffer holding all per-Gaussian gradients + named (P, n) views.
     `zero=False` skips the fill: gh_backward writes every element itself.  `storage`: use (the head of)
     this float32 buffer instead of allocating, e.g. a symmetric-memory arena (dist.PeerAllReduce)."""
-    n = P * GRAD_FLOATS_PER_GAUSSIAN
+    n = arena_floats(P)
     if storage is not None:
         if storage.dtype != torch.float32 or storage.numel() < n or not storage.is_contiguous():
-            raise RuntimeError("gradient arena storage must be a contiguous float32 tensor of at least 34 * P elements")
+            raise RuntimeError("gradient arena storage must be a contiguous float32 tensor of at least _C.arena_floats(P) elements")
         flat = storage.view(-1)[:n]
         if zero:
             flat.zero_()
@@ -141,9 +158,9 @@ def alloc_grad_arena(P: int, device: torch.device, zero: bool = True, storage: t
         alloc = torch.zeros if zero else torch.empty
         flat = alloc(n, dtype=torch.float32, device=device)
     views, off = {}, 0
-    for name, n in _GRAD_LAYOUT:
-        views[name] = flat[off:off + P * n].view(P, n)
-        off += P * n
+    for name, k in _GRAD_LAYOUT:
+        views[name] = flat[off:off + P * k].view(P, k)
+        off += _seg_floats(P, k)
     return flat, views
 
 

@@ -18,7 +18,7 @@ GH_E_NO_COLORS = 2
 GH_E_CUDA = 3
 GH_E_PREFILTERED = 4
 
-ABI_VERSION = 1
+ABI_VERSION = 2
 
 _p = C.c_void_p
 _i = C.c_int
@@ -64,9 +64,9 @@ SIGNATURES = {
         _p, _p, _p, _p, _p,                  # dL_dmean3D dL_dcov3D dL_dsh dL_dscale dL_drot
         _i, _p]),                            # debug stream
     "gh_mark_visible": (_i, [_i, _p, _p, _p, _p, _p]),
-    "gh_adam_step": (_i, [_i, _p, _p, _p, _p, _p, _p, _f, _f, _f, _i, _p, _p, _p]),
+    "gh_adam_step": (_i, [_i, _p, _p, _p, _p, _p, _p, _f, _f, _f, _i, _p, _p, _p, _p]),
     "gh_image_loss_workspace_size": (_i, [_i, _i, C.POINTER(C.c_size_t)]),
-    "gh_allreduce_p2p": (_i, [_p, _p, C.c_ulonglong, _i, _i, C.c_size_t, C.c_size_t, C.c_uint, _p, _p]),
+    "gh_allreduce_p2p": (_i, [_p, _p, C.c_ulonglong, _i, _i, C.c_size_t, C.c_size_t, C.c_uint, _p, _p, _p]),
     "gh_image_loss": (_i, [_i, _i, _p, _p, _p, _p, _p, _f, _f, _f, _f, _p, _p, _p, _p]),
     "gh_debug_export": (_i, [_i, _i, _i, _ll, _p, _p, _p, _p, _p, _p, _p, _p, _p, _p, _p, _p]),
 }

@@ -61,9 +61,11 @@ gh_adam_nan_kernel(GhAdamGroups g, unsigned int* __restrict__ flag)
 
 __global__ void __launch_bounds__(256)
 gh_adam_update_kernel(GhAdamGroups g, float beta1, float beta2, float eps,
-                      float bc1, float bc2_sqrt, const unsigned int* __restrict__ flag, int* step_state)
+                      float bc1, float bc2_sqrt, const unsigned int* __restrict__ flag,
+                      const unsigned int* __restrict__ skip_flag, int* step_state)
 {
     if (flag != nullptr && *flag != 0u) return;     // a gradient held a NaN: skip this step entirely
+    if (skip_flag != nullptr && *skip_flag != 0u) return;   // the producer of the gradients reported a failure
     if (step_state != nullptr) {
         // device-resident step count (only advanced by steps that were not skipped, like torch's state['step'])
         const int step = step_state[0] + 1;
@@ -117,11 +119,12 @@ extern "C" int gh_adam_step(int n_groups, float* const* params, const float* con
                             float* const* exp_avg, float* const* exp_avg_sq,
                             const unsigned long long* sizes, const float* lrs,
                             float beta1, float beta2, float eps, int step, int* step_state,
-                            unsigned int* nan_flag, gh_stream_t stream_)
+                            unsigned int* nan_flag, const unsigned int* skip_flag, gh_stream_t stream_)
 {
     cudaStream_t stream = (cudaStream_t)stream_;
+    gh_clear_error();
     if (n_groups <= 0 || n_groups > GH_ADAM_MAX_GROUPS || (step < 1 && step_state == nullptr) || !params || !grads || !exp_avg || !exp_avg_sq || !sizes || !lrs)
-        return GH_E_INVALID_ARG;
+        return gh_set_error(GH_E_INVALID_ARG, "gh_adam_step: bad group count / step or missing array");
     GhAdamGroups g;
     unsigned long long total = 0;
     for (int k = 0; k < GH_ADAM_MAX_GROUPS; k++) {
@@ -129,7 +132,11 @@ extern "C" int gh_adam_step(int n_groups, float* const* params, const float* con
         g.param[k] = on ? params[k] : nullptr; g.grad[k] = on ? grads[k] : nullptr;
         g.exp_avg[k] = on ? exp_avg[k] : nullptr; g.exp_avg_sq[k] = on ? exp_avg_sq[k] : nullptr;
         g.lr[k] = on ? lrs[k] : 0.f;
-        if (on) { if (!params[k] || !grads[k] || !exp_avg[k] || !exp_avg_sq[k]) return GH_E_INVALID_ARG; total += sizes[k]; }
+        if (on) {
+            if (!params[k] || !grads[k] || !exp_avg[k] || !exp_avg_sq[k])
+                return gh_set_error(GH_E_INVALID_ARG, "gh_adam_step: NULL parameter / gradient / moment pointer");
+            total += sizes[k];
+        }
         g.end[k] = total;
     }
     g.n = n_groups;
@@ -142,11 +149,13 @@ extern "C" int gh_adam_step(int n_groups, float* const* params, const float* con
     const unsigned long long want = (largest / 4 + 255) / 256;
     const dim3 grid((unsigned int)(want < 1 ? 1 : (want > 148ull * 8 ? 148ull * 8 : want)), (unsigned int)n_groups);
     if (nan_flag) {
-        if (cudaMemsetAsync(nan_flag, 0, sizeof(unsigned int), stream) != cudaSuccess) return GH_E_CUDA;
+        if (cudaMemsetAsync(nan_flag, 0, sizeof(unsigned int), stream) != cudaSuccess)
+            return gh_set_error(GH_E_CUDA, "gh_adam_step: memset of the NaN flag failed");
         gh_adam_nan_kernel<<<grid, 256, 0, stream>>>(g, nan_flag);
         gh_count_launches(1);
     }
-    gh_adam_update_kernel<<<grid, 256, 0, stream>>>(g, beta1, beta2, eps, (float)bc1, (float)sqrt(bc2), nan_flag, step_state);
+    gh_adam_update_kernel<<<grid, 256, 0, stream>>>(g, beta1, beta2, eps, (float)bc1, (float)sqrt(bc2), nan_flag, skip_flag, step_state);
     gh_count_launches(1);
-    return cudaGetLastError() == cudaSuccess ? GH_OK : GH_E_CUDA;
+    const cudaError_t e = cudaGetLastError();
+    return e == cudaSuccess ? GH_OK : gh_set_error(GH_E_CUDA, cudaGetErrorString(e));
 }

@@ -4,17 +4,22 @@
 #include "gh_kernels.h"
 #include "../../include/gh_rasterizer.h"
 
+#include <atomic>
 #include <cstdio>
 #include <cstring>
+#include <mutex>
+
+// per-thread error message shared by every entry point of the library (gh_kernels.h)
+static thread_local char g_err[512] = "";
+void gh_clear_error() { g_err[0] = 0; }
+int gh_set_error(int code, const char* msg) {
+    std::snprintf(g_err, sizeof(g_err), "%s", msg ? msg : "");
+    return code;
+}
 
 namespace {
 
-thread_local char g_err[512] = "";
-
-int gh_fail(int code, const char* msg) {
-    std::snprintf(g_err, sizeof(g_err), "%s", msg);
-    return code;
-}
+int gh_fail(int code, const char* msg) { return gh_set_error(code, msg); }
 
 int gh_check_cuda(cudaError_t e, const char* what) {
     if (e == cudaSuccess) return GH_OK;
@@ -33,27 +38,36 @@ int gh_check_cuda(cudaError_t e, const char* what) {
 // ---- optional per-stage device timing (bench / roofline only; off by default) -------------------
 enum { GH_ST_PREPROCESS = 0, GH_ST_TILE_SCAN, GH_ST_EMIT, GH_ST_TILE_SORT, GH_ST_BLEND_FWD, GH_ST_BLEND_BWD,
        GH_ST_PREPROCESS_BWD, GH_ST_COUNT };
-bool g_timing = false;
+// The only process-wide state of the library: the launch counter (atomic) and the diagnostic stage
+// timer (a mutex guards its sums; events are created per stage on the caller's current device, so the
+// forward thread, autograd's backward thread and several devices can use it at once).
+std::atomic<bool> g_timing{false};
+std::mutex g_timing_mu;
 double g_stage_ms[GH_ST_COUNT] = {0};
 unsigned long long g_stage_calls[GH_ST_COUNT] = {0};
-unsigned long long g_launches = 0;     // kernels launched by this library since load
-cudaEvent_t g_ev0 = nullptr, g_ev1 = nullptr;
+std::atomic<unsigned long long> g_launches{0};     // kernels launched by this library since load
 
 struct GhStageTimer {
-    int stage; cudaStream_t stream; unsigned long long l0;
-    GhStageTimer(int st, cudaStream_t s) : stage(st), stream(s), l0(g_launches) {
-        if (g_timing) {
-            if (!g_ev0) { cudaEventCreate(&g_ev0); cudaEventCreate(&g_ev1); }
-            cudaEventRecord(g_ev0, stream);
+    int stage; cudaStream_t stream; unsigned long long l0; bool on;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    GhStageTimer(int st, cudaStream_t s) : stage(st), stream(s), l0(g_launches.load()), on(g_timing.load()) {
+        if (on) {
+            on = (cudaEventCreate(&ev0) == cudaSuccess) && (cudaEventCreate(&ev1) == cudaSuccess);
+            if (on) cudaEventRecord(ev0, stream);
         }
     }
     ~GhStageTimer() {
-        if (g_timing && g_launches != l0) {      // a stage that launched nothing (in-kernel tile sort) is not a stage
-            cudaEventRecord(g_ev1, stream);
-            cudaEventSynchronize(g_ev1);
+        if (on && g_launches.load() != l0) {     // a stage that launched nothing (in-kernel tile sort) is not a stage
+            cudaEventRecord(ev1, stream);
+            cudaEventSynchronize(ev1);
             float ms = 0.f;
-            if (cudaEventElapsedTime(&ms, g_ev0, g_ev1) == cudaSuccess) { g_stage_ms[stage] += ms; g_stage_calls[stage] += 1; }
+            if (cudaEventElapsedTime(&ms, ev0, ev1) == cudaSuccess) {
+                std::lock_guard<std::mutex> lk(g_timing_mu);
+                g_stage_ms[stage] += ms; g_stage_calls[stage] += 1;
+            }
         }
+        if (ev0) cudaEventDestroy(ev0);
+        if (ev1) cudaEventDestroy(ev1);
     }
 };
 
@@ -88,20 +102,22 @@ __global__ void gh_export_geom_kernel(int P, const GhGeo* __restrict__ geo, floa
 
 }  // namespace
 
-void gh_count_launches(int n) { g_launches += (unsigned long long)n; }
+void gh_count_launches(int n) { g_launches.fetch_add((unsigned long long)n); }
 
 extern "C" {
 
-int gh_abi_version(void) { return 1; }
+int gh_abi_version(void) { return 2; }
 
-unsigned long long gh_kernel_launch_count(void) { return g_launches; }
+unsigned long long gh_kernel_launch_count(void) { return g_launches.load(); }
 
 void gh_stage_timing_enable(int on) {
-    g_timing = (on != 0);
+    std::lock_guard<std::mutex> lk(g_timing_mu);
+    g_timing.store(on != 0);
     for (int i = 0; i < GH_ST_COUNT; i++) { g_stage_ms[i] = 0.0; g_stage_calls[i] = 0; }
 }
 
 int gh_stage_timing_read(double* ms_sum, unsigned long long* calls, int capacity) {
+    std::lock_guard<std::mutex> lk(g_timing_mu);
     const int n = capacity < GH_ST_COUNT ? capacity : GH_ST_COUNT;
     for (int i = 0; i < n; i++) { if (ms_sum) ms_sum[i] = g_stage_ms[i]; if (calls) calls[i] = g_stage_calls[i]; }
     return GH_ST_COUNT;

@@ -244,30 +244,6 @@ gh_segment_sort_kernel(const uint2* __restrict__ seg, const GhCtrl* __restrict__
     }
 }
 
-// SMEM_KEYS: capacity of the shared staging buffer; handles tiles with lo < n <= hi.
-// Tiles longer than the buffer are sorted in place in global memory by the same network.
-template <int NT>
-__global__ void __launch_bounds__(NT)
-gh_tile_sort_kernel(const uint2* __restrict__ ranges, uint64_t* inst,
-                    uint32_t lo, uint32_t hi, uint32_t smem_keys)
-{
-    extern __shared__ __align__(16) uint64_t skeys[];
-    const uint2 rg = ranges[blockIdx.x];
-    const uint32_t n = rg.y - rg.x;
-    if (n <= lo || n > hi || n < 2) return;
-    uint64_t* g = inst + rg.x;
-    const int tid = threadIdx.x;
-    if (n <= smem_keys) {
-        for (uint32_t i = tid; i < n; i += NT) skeys[i] = g[i];
-        __syncthreads();
-        gh_bitonic_sort(skeys, n, tid, NT);
-        for (uint32_t i = tid; i < n; i += NT) g[i] = skeys[i];
-    } else {
-        __syncthreads();
-        gh_bitonic_sort(g, n, tid, NT);
-    }
-}
-
 }  // namespace
 
 void gh_launch_tile_scan(int T, GhImgWS img, cudaStream_t stream)

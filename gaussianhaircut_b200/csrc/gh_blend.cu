@@ -223,7 +223,8 @@ gh_blend_forward_kernel(const uint2* __restrict__ ranges, uint64_t* inst,
     // Sort this tile's bucket by (depth bits, Gaussian index) right here when it fits the staging buffers
     // (<= 2048 records = 16 KB): the sort is latency/barrier bound, the blend is issue bound, and as
     // one kernel the two overlap across the CTAs of an SM.  The sorted bucket is written back for the
-    // backward pass.  Longer lists were sorted by gh_tile_sort_kernel before this launch.
+    // backward pass.  Longer lists were sorted by gh_tile_split_long_kernel + gh_segment_sort_kernel
+    // (gh_binning.cu) before this launch.
     if (n >= 2 && n <= (int)GH_INKERNEL_SORT_MAX) {
         uint64_t* sbase = reinterpret_cast<uint64_t*>(&st.g0[0][0]);     // g0 + g1 = 16 KB contiguous
         uint64_t* spong = reinterpret_cast<uint64_t*>(&st.feat[0][0]);   // next 16 KB (feat is 20 KB)

@@ -172,36 +172,7 @@ __device__ __forceinline__ float gh_power(float dx, float dy, float ca, float cb
     return GH_FMA(s, -0.5f, -t5);   // SASS: FFMA R, s, -0.5, -t5
 }
 
-// Conservative test: can a Gaussian reach alpha >= 1/255 on ANY pixel of the integer pixel
-// rectangle [rx0,rx1] x [ry0,ry1]?  Returns true when in doubt.  Skipping a Gaussian that fails
-// this test cannot change any pixel: every pixel of the rectangle would hit the reference's
-// `alpha < 1/255 -> continue` (forward.cu:370) for it.
-__device__ __forceinline__ bool gh_cull_hit(const GhGeo& g, float rx0, float rx1, float ry0, float ry1) {
-    // d = mean - pixel  (same sign convention as the blend)
-    const float dx0 = g.x - rx1, dx1 = g.x - rx0;
-    const float dy0 = g.y - ry1, dy1 = g.y - ry0;
-    const bool inside = (dx0 <= 0.f) & (dx1 >= 0.f) & (dy0 <= 0.f) & (dy1 >= 0.f);
-    const float a = g.ca, b = g.cb, c = g.cc;
-    // minimum of q(d) = a dx^2 + 2 b dx dy + c dy^2 over the box: on one of the four edges
-    const float ia = __frcp_rn(a), ic = __frcp_rn(c);
-    float qmin;
-    {
-        float X = dx0, Y = fminf(fmaxf(-b * X * ic, dy0), dy1);
-        qmin = a * X * X + 2.f * b * X * Y + c * Y * Y;
-        X = dx1; Y = fminf(fmaxf(-b * X * ic, dy0), dy1);
-        qmin = fminf(qmin, a * X * X + 2.f * b * X * Y + c * Y * Y);
-        Y = dy0; X = fminf(fmaxf(-b * Y * ia, dx0), dx1);
-        qmin = fminf(qmin, a * X * X + 2.f * b * X * Y + c * Y * Y);
-        Y = dy1; X = fminf(fmaxf(-b * Y * ia, dx0), dx1);
-        qmin = fminf(qmin, a * X * X + 2.f * b * X * Y + c * Y * Y);
-    }
-    const float mx = fmaxf(fabsf(dx0), fabsf(dx1)), my = fmaxf(fabsf(dy0), fabsf(dy1));
-    const float slack = 1e-3f + 2e-5f * (fabsf(a) * mx * mx + fabsf(c) * my * my + 2.f * fabsf(b) * mx * my);
-    const bool miss = (0.5f * qmin > g.thr + slack);   // false for NaN
-    return inside | (g.pd == 0.f) | !miss;
-}
-
-// ---- per-tile sort network (used by the forward blend CTA for its own list and by gh_tile_sort_kernel)
+// ---- per-tile sort network (used by the forward blend CTA for its own list and by gh_segment_sort_kernel)
 #define GH_INKERNEL_SORT_MAX 2048u
 // Normalised bitonic network (every comparator puts the smaller key at the lower index), so
 // elements beyond n behave as +inf without being materialised: a comparator whose upper index

@@ -424,7 +424,8 @@ gh_loss_finalize_kernel(GhLossParams prm, const double* __restrict__ sums, float
 
 extern "C" int gh_image_loss_workspace_size(int width, int height, size_t* bytes)
 {
-    if (width <= 0 || height <= 0 || !bytes) return GH_E_INVALID_ARG;
+    gh_clear_error();
+    if (width <= 0 || height <= 0 || !bytes) return gh_set_error(GH_E_INVALID_ARG, "gh_image_loss_workspace_size: bad width/height");
     *bytes = GH_LS_COUNT * sizeof(double) + (size_t)9 * width * height * sizeof(float);
     return GH_OK;
 }
@@ -435,11 +436,13 @@ extern "C" int gh_image_loss(int width, int height, const float* out_color, cons
                              void* workspace, float* losses, float* dL_dout, gh_stream_t stream_)
 {
     cudaStream_t stream = (cudaStream_t)stream_;
+    gh_clear_error();
     if (width <= 0 || height <= 0 || !out_color || !gt_image || !gt_mask || !gt_orient_angle || !gt_orient_conf ||
         !workspace || !losses || !dL_dout)
-        return GH_E_INVALID_ARG;
-    if ((size_t)workspace & 7) return GH_E_INVALID_ARG;
-    if ((long long)width * height > (1ll << 27)) return GH_E_INVALID_ARG;      // 32-bit pixel offsets inside the kernels
+        return gh_set_error(GH_E_INVALID_ARG, "gh_image_loss: bad size or missing pointer");
+    if ((size_t)workspace & 7) return gh_set_error(GH_E_INVALID_ARG, "gh_image_loss: workspace must be 8-byte aligned");
+    if ((long long)width * height > (1ll << 27))      // 32-bit pixel offsets inside the kernels
+        return gh_set_error(GH_E_INVALID_ARG, "gh_image_loss: image larger than 2^27 pixels");
     GhLossParams prm;
     prm.W = width; prm.H = height;
     prm.l_dl1 = lambda_dl1; prm.l_dssim = lambda_dssim; prm.l_dmask = lambda_dmask; prm.l_dorient = lambda_dorient;
@@ -451,7 +454,8 @@ extern "C" int gh_image_loss(int width, int height, const float* out_color, cons
     double* sums = reinterpret_cast<double*>(workspace);
     float* dmaps = reinterpret_cast<float*>(sums + GH_LS_COUNT);
     const size_t plane = (size_t)width * height;
-    if (cudaMemsetAsync(sums, 0, GH_LS_COUNT * sizeof(double), stream) != cudaSuccess) return GH_E_CUDA;
+    if (cudaMemsetAsync(sums, 0, GH_LS_COUNT * sizeof(double), stream) != cudaSuccess)
+        return gh_set_error(GH_E_CUDA, "gh_image_loss: memset of the partial sums failed");
     const int rb = (int)((plane + 255) / 256 < 148u * 8u ? (plane + 255) / 256 : 148u * 8u);
     gh_loss_presum_kernel<<<rb, 256, 0, stream>>>(gt_orient_conf, plane, sums);
     const dim3 grid((width + GH_LT - 1) / GH_LT, (height + GH_LT - 1) / GH_LT), block(256);
@@ -462,5 +466,6 @@ extern "C" int gh_image_loss(int width, int height, const float* out_color, cons
     gh_loss_ssim_bwd_kernel<4><<<grid, block, 0, stream>>>(prm, out_color, gt_image, gt_mask, dmaps, dL_dout);
     gh_loss_finalize_kernel<<<rb, 256, 0, stream>>>(prm, sums, losses, dL_dout);
     gh_count_launches(5);
-    return cudaGetLastError() == cudaSuccess ? GH_OK : GH_E_CUDA;
+    const cudaError_t e = cudaGetLastError();
+    return e == cudaSuccess ? GH_OK : gh_set_error(GH_E_CUDA, cudaGetErrorString(e));
 }

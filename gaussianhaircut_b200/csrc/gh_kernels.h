@@ -47,5 +47,10 @@ void gh_launch_preprocess_backward(int P, const float* means3D, const int* radii
                                    float* dL_dmean3D, float* dL_dcov3D, float* dL_dscale, float* dL_drot,
                                    cudaStream_t stream);
 
+// per-thread error message behind gh_last_error(): every extern "C" entry point clears it on entry and
+// sets it before returning a GH_E_* code (defined in gh_api.cu)
+void gh_clear_error();
+int gh_set_error(int code, const char* msg);
+
 // kernels launched outside gh_api.cu (optimizer, image losses) report themselves to gh_kernel_launch_count()
 void gh_count_launches(int n);

@@ -135,6 +135,10 @@ gh_preprocess_kernel(int P,
         const float my_radius = ceilf(GH_MUL(GH_SQRT(lam), 3.0f));
         const float pix_x = gh_ndc2pix(projx, W), pix_y = gh_ndc2pix(projy, H);
         const int ri = __float2int_rz(my_radius);
+        // NaN covariance -> NaN radius -> 0: the reference counts such a Gaussian in tiles_touched but never
+        // emits its key (duplicateWithKeys tests radii > 0), leaving an uninitialised record in the list;
+        // dropping it here keeps the histogram and the emit consistent
+        if (ri <= 0) break;
         int minx, miny, maxx, maxy;
         gh_get_rect(pix_x, pix_y, ri, gx, gy, minx, miny, maxx, maxy);
         if ((maxx - minx) * (maxy - miny) == 0) break;

@@ -37,13 +37,13 @@ def trainable_slice(flat: torch.Tensor, num_gaussians: int, call_shape: str = "n
     """The contiguous prefix of the gradient arena that the optimizer consumes.
 
     `native` (the op computes covariances from scales/rotations): rotations, colors, opacity,
-    means3D, scales = the first 21 floats per Gaussian; means2D (densification statistics only) and
-    the conic / cov3D segments behind
-    it stay zero and need not travel.  Any other call shape: the whole arena.
+    means3D, scales = the first 21 floats per Gaussian (each segment padded to a multiple of 4 floats,
+    `_C.trainable_floats`); means2D (densification statistics only) and the conic / cov3D segments behind
+    it need not travel.  Any other call shape: the whole arena.
     """
     from . import _C
     if call_shape == "native":
-        return flat[: num_gaussians * _C.GRAD_FLOATS_TRAINABLE_NATIVE]
+        return flat[: _C.trainable_floats(num_gaussians)]
     return flat
 
 
@@ -85,15 +85,18 @@ class PeerAllReduce:
     """Sum a float32 gradient arena over the GPUs of one node with `gh_allreduce_p2p`: one kernel per
     rank that reads and writes the peers' arenas through NVLink (symmetric memory), instead of NCCL.
 
-        par = PeerAllReduce(34 * P, device)                      # once; collective (rendezvous)
+        par = PeerAllReduce(_C.arena_floats(P), device)          # once; collective (rendezvous)
         flat, grads, _ = _C.rasterize_gaussians_backward_arena(..., arena_storage=par.buffer)
-        par.all_reduce(n_floats=21 * P)                          # in place, on the current stream
-        optimizer.step(...)                                      # stream order is enough: no host sync
+        par.all_reduce(n_floats=_C.trainable_floats(P))          # in place, on the current stream
+        optimizer.step(..., skip_flags=(par.error_flag,), nan_flag_in=par.nan_flag)   # stream order is enough
 
     `use_multicast`: None = choose by world size (NVLS multimem from 8 GPUs up, when the allocation has a
     multicast mapping), True / False = force.  Every rank must call `all_reduce` the same number of times
-    with the same range.  `ok()` (host sync)
-    tells whether every peer arrived at every barrier so far."""
+    with the same range.  A peer that does not arrive within GH_ALLREDUCE_TIMEOUT_MS (default 30 s) makes the
+    kernel SKIP the reduction and raise `error_flag` (device uint32, sticky); hand it to the optimizer as a
+    skip flag (no host sync) or poll `ok()` (host sync; `all_reduce(check=True)` raises).  `nan_flag`
+    (device uint32, identical on all ranks) tells whether the reduced range holds a NaN: the optimizer's NaN
+    guard without its own pass over the gradients."""
 
     def __init__(self, numel: int, device: torch.device, group: Optional[dist.ProcessGroup] = None,
                  use_multicast: Optional[bool] = None):
@@ -113,7 +116,9 @@ class PeerAllReduce:
             self.buffer = symm_mem.empty(n, dtype=torch.float32, device=device)
             self._flags = symm_mem.empty(64, dtype=torch.int32, device=device)
             self._flags.zero_()
-            self._local = torch.zeros(4, dtype=torch.int32, device=device)
+            self.buffer.zero_()                                     # segment padding never holds garbage
+            self._local = torch.zeros(8, dtype=torch.int32, device=device)
+            self.nan_flag = torch.zeros(1, dtype=torch.int32, device=device)
             hb = symm_mem.rendezvous(self.buffer, self.group)
             hf = symm_mem.rendezvous(self._flags, self.group)
             torch.cuda.synchronize(device)
@@ -130,7 +135,12 @@ class PeerAllReduce:
         self._lib = _capi.load()
         self._capi = _capi
 
-    def all_reduce(self, n_floats: Optional[int] = None, offset_floats: int = 0) -> None:
+    @property
+    def error_flag(self) -> torch.Tensor:
+        """Device uint32 (view): non-zero once any all-reduce of this object failed (peer timeout)."""
+        return self._local[2:3]
+
+    def all_reduce(self, n_floats: Optional[int] = None, offset_floats: int = 0, check: bool = False) -> None:
         import ctypes as C
         n = self.buffer.numel() - offset_floats if n_floats is None else int(n_floats)
         n = (n + 3) // 4 * 4
@@ -142,7 +152,10 @@ class PeerAllReduce:
             self._capi.check(self._lib.gh_allreduce_p2p(
                 self._bufs, self._flagptrs, C.c_ulonglong(self.multicast), self.rank, self.world,
                 C.c_size_t(offset_floats), C.c_size_t(n), C.c_uint(self._epoch),
-                C.c_void_p(self._local.data_ptr()), stream))
+                C.c_void_p(self._local.data_ptr()), C.c_void_p(self.nan_flag.data_ptr()), stream))
+        if check and not self.ok():
+            raise RuntimeError("PeerAllReduce: a peer did not reach the barrier in time; the reduction was skipped "
+                               "and the gradient arena is undefined (GH_ALLREDUCE_TIMEOUT_MS)")
 
     def ok(self) -> bool:
         return int(self._local[2].item()) == 0

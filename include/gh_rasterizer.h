@@ -20,9 +20,13 @@
  * Conventions
  *   - every pointer is a DEVICE pointer to contiguous float32 / int32 data unless stated otherwise;
  *     NULL means "absent optional" (the reference's empty-tensor convention, __init__.py:210-222);
- *   - the library allocates nothing and keeps no state between calls; the caller owns all buffers
- *     (outputs and the three opaque workspaces) and passes the CUDA stream explicitly
- *     (the reference uses the legacy default stream implicitly);
+ *   - the library allocates no device memory and keeps no per-call state: the caller owns all buffers
+ *     (outputs and the three opaque workspaces) and passes the CUDA stream explicitly (the reference
+ *     uses the legacy default stream implicitly).  Entry points are re-entrant and may be called from
+ *     several host threads (PyTorch calls gh_backward from its autograd thread) and for several
+ *     devices.  The only process-wide state is diagnostic: an atomic kernel-launch counter, the
+ *     optional stage timer (mutex-guarded sums, events created per stage on the caller's device) and
+ *     the per-thread message behind gh_last_error();
  *   - matrices use the reference's row-vector (transposed) convention: viewmatrix[12..14] is the
  *     translation (auxiliary.h:58-66);
  *   - return value: 0 on success, a GH_E_* code otherwise; gh_last_error() gives the message for the
@@ -177,13 +181,16 @@ int gh_debug_export(
  * (zero-initialised) and the step count lives on the device (advanced only by steps that were not skipped).
  * nan_flag (device uint, may be NULL): when given, the step is skipped on the device if any gradient
  * holds a NaN and the flag is left non-zero (the reference's NaN guard without its host syncs).
+ * skip_flag (device uint, may be NULL, read only): the step is also skipped when *skip_flag != 0 -- pass
+ * the error word (local_sync + 2) or the nan_out word of gh_allreduce_p2p so that a failed or poisoned
+ * gradient exchange never reaches the parameters.
  */
 #define GH_ADAM_MAX_GROUPS 8
 int gh_adam_step(int n_groups, float* const* params, const float* const* grads,
                  float* const* exp_avg, float* const* exp_avg_sq,
                  const unsigned long long* sizes, const float* lrs,
                  float beta1, float beta2, float eps, int step, int* step_state,
-                 unsigned int* nan_flag, gh_stream_t stream);
+                 unsigned int* nan_flag, const unsigned int* skip_flag, gh_stream_t stream);
 
 /*
  * "Next" row: the image-space losses of the appearance stage, forward + backward in
@@ -211,17 +218,22 @@ int gh_image_loss(int width, int height, const float* out_color, const float* gt
  * all ranks, in place, with one kernel per rank that reads and writes its peers' copies through NVLink.
  * Replaces the NCCL all-reduce of the gradient arena; every rank of the group must make the same call.
  * peer_bufs / peer_flags: HOST arrays of `world` device addresses (this process's mappings of every
- *   rank's buffer and of every rank's flag block; flag block = uint32[2 * world], zero-initialised once).
+ *   rank's buffer and of every rank's flag block; flag block = uint32[3 * world], zero-initialised once).
  * multicast_buf: NVLS multicast mapping of the buffer, or 0 (then plain peer loads/stores are used).
  * offset_floats, n_floats: the range to reduce (multiples of 4; buffers 16-byte aligned).
  * epoch: 1, 2, 3, ... strictly increasing per call on every rank.
- * local_sync: device uint32[4] of this rank, zero-initialised once; word 2 becomes non-zero if a peer
- *   did not arrive within the (bounded) spin, in which case the result is undefined.
+ * local_sync: device uint32[8] of this rank, zero-initialised once; word 2 (sticky) becomes non-zero if a
+ *   peer did not arrive within the wall-clock bound (GH_ALLREDUCE_TIMEOUT_MS, default 30000): the reduction
+ *   of that call is then SKIPPED on this rank (no partial sums) and the buffer content is undefined.
+ * nan_out (device uint, may be NULL): set to 1 if the SUM holds a NaN anywhere in the range (identical on
+ *   every rank: the per-slice findings are exchanged with the exit barrier), else 0.
+ * Tunables (environment, read per call): GH_ALLREDUCE_THREADS, GH_ALLREDUCE_CTAS_PER_SM,
+ *   GH_ALLREDUCE_UNROLL (NVLS path: 16-byte requests in flight per thread).
  */
 int gh_allreduce_p2p(const unsigned long long* peer_bufs, const unsigned long long* peer_flags,
                      unsigned long long multicast_buf, int rank, int world,
                      size_t offset_floats, size_t n_floats, unsigned int epoch,
-                     unsigned int* local_sync, gh_stream_t stream);
+                     unsigned int* local_sync, unsigned int* nan_out, gh_stream_t stream);
 
 #ifdef __cplusplus
 }

@@ -11,7 +11,9 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 if ROOT not in sys.path:
     sys.path.insert(0, ROOT)
 
-from gaussianhaircut_b200 import synth  # noqa: E402
+if os.path.join(ROOT, "oracle") not in sys.path:
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+import synth  # noqa: E402  (oracle/synth.py: seeded scenes, cameras, the caller-preamble restatement)
 
 
 def ref_module():

@@ -56,7 +56,8 @@ def main():
     gm = importlib.util.module_from_spec(spec)
     spec.loader.exec_module(gm)
     from utils.sh_utils import eval_sh          # reference module
-    from gaussianhaircut_b200 import synth       # only for the seeded scene + camera matrices
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import synth       # only for the seeded scene + camera matrices
 
     scene = synth.make_strand_scene(20, seed=7)
     W, H = 200, 120

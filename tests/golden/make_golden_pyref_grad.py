@@ -32,7 +32,8 @@ def main():
     gm = importlib.util.module_from_spec(spec)
     spec.loader.exec_module(gm)
     from utils.sh_utils import eval_sh
-    from gaussianhaircut_b200 import synth
+    sys.path.insert(0, os.path.join(base.ROOT, "oracle"))
+    import synth
 
     strands, seed, cam_k, W, H = 6, 5, 13, 160, 96
     scene = synth.make_strand_scene(strands, seed=seed)

@@ -133,20 +133,25 @@ def test_front_door_surface():
 
 def test_grad_arena_layout():
     from gaussianhaircut_b200 import _C
-    P = 7
-    flat, g = _C.alloc_grad_arena(P, torch.device("cpu"))
-    assert flat.numel() == P * 34 and _C.GRAD_FLOATS_PER_GAUSSIAN == 34
-    assert g["rotations"].data_ptr() % 16 == 0          # stored as one float4 per Gaussian
     shapes = {"rotations": 4, "conic": 4, "colors": 10, "cov3D": 6, "means3D": 3, "means2D": 3, "scales": 3, "opacity": 1}
-    assert (g["conic"].data_ptr() - flat.data_ptr()) % 16 == 0 and g["rotations"].data_ptr() == flat.data_ptr()
-    assert _C.GRAD_FLOATS_TRAINABLE_NATIVE == 21
-    assert g["conic"].data_ptr() - flat.data_ptr() == 24 * P * 4
-    seen = 0
-    for k, n in shapes.items():
-        assert tuple(g[k].shape) == (P, n)
-        g[k].fill_(1.0)
-        seen += P * n
-    assert float(flat.sum()) == seen == flat.numel()     # the views tile the arena exactly, no overlap
+    for P in (8, 7, 1, 13):
+        flat, g = _C.alloc_grad_arena(P, torch.device("cpu"))
+        assert _C.GRAD_FLOATS_PER_GAUSSIAN == 34 and _C.GRAD_FLOATS_TRAINABLE_NATIVE == 21
+        assert flat.numel() == _C.arena_floats(P) and P * 34 <= flat.numel() <= P * 34 + 3 * 8
+        if P % 4 == 0:
+            assert flat.numel() == P * 34 and _C.trainable_floats(P) == 21 * P
+            assert g["conic"].data_ptr() - flat.data_ptr() == 24 * P * 4
+        assert g["rotations"].data_ptr() == flat.data_ptr()
+        seen = 0
+        for k, n in shapes.items():
+            assert tuple(g[k].shape) == (P, n)
+            assert (g[k].data_ptr() - flat.data_ptr()) % 16 == 0, k      # every segment 16-byte aligned for any P
+            g[k].fill_(1.0)
+            seen += P * n
+        assert float(flat.sum()) == seen                  # the views do not overlap; only segment padding is left
+        # a 4-float-granular all-reduce of the trainable prefix never reaches the means2D segment
+        assert _C.trainable_floats(P) % 4 == 0
+        assert g["means2D"].data_ptr() - flat.data_ptr() == _C.trainable_floats(P) * 4
 
 
 def test_autograd_wiring_with_fake_native(monkeypatch):
@@ -210,7 +215,8 @@ gd.allreduce_gradient_arena(flat)                      # ONE collective for ever
 gathered = [torch.zeros_like(mine) for _ in range(world)]
 dist.all_gather(gathered, mine)
 assert torch.allclose(flat, sum(gathered)), "arena all-reduce != sum of per-rank gradients"
-assert torch.allclose(g["colors"], sum(x[4 * P:14 * P].view(P, 10) for x in gathered))   # views see the result
+o = (4 * P + 3) // 4 * 4
+assert torch.allclose(g["colors"], sum(x[o:o + 10 * P].view(P, 10) for x in gathered))   # views see the result
 acc, den, mx = torch.full((P, 1), float(rank + 1)), torch.ones(P, 1), torch.full((P,), float(rank))
 gd.allreduce_densification_stats(acc, den, mx)
 assert float(acc[0]) == sum(range(1, world + 1)) and float(den[0]) == world and float(mx[0]) == world - 1
@@ -256,7 +262,11 @@ def test_trainable_slice_and_peer_allreduce_guards():
         assert g[k].data_ptr() >= flat.data_ptr() + 21 * P * 4
     assert gd.trainable_slice(flat, P, "render").numel() == flat.numel()
     with pytest.raises(RuntimeError, match="process group"):
-        gd.PeerAllReduce(34 * P, torch.device("cpu"))
+        gd.PeerAllReduce(_C.arena_floats(P), torch.device("cpu"))
+    # odd P: the prefix is padded, never spills into means2D
+    flat7, g7 = _C.alloc_grad_arena(7, torch.device("cpu"))
+    sl7 = gd.trainable_slice(flat7, 7, "native")
+    assert sl7.numel() % 4 == 0 and sl7.data_ptr() + sl7.numel() * 4 == g7["means2D"].data_ptr()
     # caller-owned arena storage
     store = torch.zeros(34 * P + 5)
     flat2, g2 = _C.alloc_grad_arena(P, torch.device("cpu"), zero=False, storage=store)

@@ -97,9 +97,9 @@ def test_oracle_matches_reference_python_stage1():
 
 
 def test_synth_preamble_matches_reference_python():
-    """gaussianhaircut_b200.synth restates the caller preamble for the bench/tests; pin it too."""
+    """oracle/synth.py restates the caller preamble for the bench/tests; pin it too."""
     import torch
-    from gaussianhaircut_b200 import synth
+    import synth
     d = np.load(os.path.join(ROOT, "tests", "golden", "pyref_stage1.npz"))
     scene = synth.make_strand_scene(int(d["strands"]), seed=int(d["seed"]))
     cam = synth.make_camera(int(d["cam_k"]), int(d["W"]), int(d["H"]))
@@ -118,7 +118,7 @@ def test_synth_preamble_gradients_match_reference_python():
     differentiated on the CPU (tests/golden/make_golden_pyref_grad.py)."""
     import torch
     import torch.nn.functional as F
-    from gaussianhaircut_b200 import synth
+    import synth
     d = np.load(os.path.join(ROOT, "tests", "golden", "pyref_stage1_grad.npz"))
     scene = synth.make_strand_scene(int(d["strands"]), seed=int(d["seed"]))
     cam = dict(synth.make_camera(int(d["cam_k"]), int(d["W"]), int(d["H"])))

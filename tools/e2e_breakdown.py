@@ -3,7 +3,8 @@ import os, sys, time
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "oracle"))
 import torch
-from gaussianhaircut_b200 import synth
+sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "oracle"))
+import synth
 impl = sys.argv[1] if len(sys.argv) > 1 else "mine"
 if impl == "mine":
     import gaussianhaircut_b200 as mod

@@ -23,7 +23,9 @@ def main():
     ap.add_argument("--res", default="1920x1080")
     ap.add_argument("--max-tiles", type=int, default=600)
     args = ap.parse_args()
-    from gaussianhaircut_b200 import _C, synth
+    from gaussianhaircut_b200 import _C
+    sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "oracle"))
+    import synth
     W, H = map(int, args.res.split("x"))
     dev = torch.device("cuda:0")
     scene = synth.make_strand_scene(args.strands, seed=0)

@@ -3,7 +3,9 @@ import os, sys
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 import torch
-from gaussianhaircut_b200 import _C, synth
+from gaussianhaircut_b200 import _C
+sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "oracle"))
+import synth
 dev = torch.device("cuda:0")
 W, H = 1920, 1080
 scene = synth.make_strand_scene(int(sys.argv[1]) if len(sys.argv) > 1 else 20000, seed=0)
