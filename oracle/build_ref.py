@@ -40,8 +40,36 @@ EXT_SUFFIX = sysconfig.get_config_var("EXT_SUFFIX")
 SO_PATH = os.path.join(OUT_PKG, "_C" + EXT_SUFFIX)
 
 
+REF_SRC = "/root/reference/src"
+OUT_SRC = os.path.join(HERE, "_ref", "src")
+# the reference's Python callers of the hot path (pure Python: "installing" them is a copy; oracle/_ref is
+# git-ignored build output, so nothing of this enters the history) -- used by oracle/ref_python.py to run
+# render() / render_hair() unmodified on the GPU box, where /root/reference does not exist
+PY_STAGE = ("gaussian_renderer/__init__.py", "scene", "utils", "arguments/__init__.py")
+
+
 def ref_available() -> bool:
     return os.path.isdir(REF_EXT)
+
+
+def stage_python(verbose: bool = True) -> str:
+    """Copy the reference's pure-Python render path next to the compiled extension (oracle/_ref/src)."""
+    if not os.path.isdir(REF_SRC):
+        return OUT_SRC
+    for rel in PY_STAGE:
+        src = os.path.join(REF_SRC, rel)
+        dst = os.path.join(OUT_SRC, rel)
+        if os.path.isdir(src):
+            os.makedirs(dst, exist_ok=True)
+            for f in sorted(os.listdir(src)):
+                if f.endswith(".py"):
+                    shutil.copyfile(os.path.join(src, f), os.path.join(dst, f))
+        elif os.path.isfile(src):
+            os.makedirs(os.path.dirname(dst), exist_ok=True)
+            shutil.copyfile(src, dst)
+    if verbose:
+        print("[oracle/_ref] staged the reference's Python render path under", OUT_SRC, flush=True)
+    return OUT_SRC
 
 
 def is_built() -> bool:
@@ -70,7 +98,8 @@ def build(verbose: bool = True, force: bool = False) -> str:
         os.path.join(REF_EXT, "rasterize_points.cu"),
         os.path.join(REF_EXT, "ext.cpp"),
     ]
-    deps = srcs + [os.path.join(HERE, "glm_shim", "glm", "glm.hpp"), os.path.abspath(__file__)]
+    stage_python(verbose=False)
+    deps = srcs + [os.path.join(HERE, "glm_shim", "glm", "glm.hpp")]
     if is_built() and not force:
         newest = max(os.path.getmtime(p) for p in deps)
         if os.path.getmtime(SO_PATH) >= newest:
