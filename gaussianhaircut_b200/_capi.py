@@ -68,6 +68,29 @@ SIGNATURES = {
     "gh_image_loss_workspace_size": (_i, [_i, _i, C.POINTER(C.c_size_t)]),
     "gh_allreduce_p2p": (_i, [_p, _p, C.c_ulonglong, _i, _i, C.c_size_t, C.c_size_t, C.c_uint, _p, _p, _p]),
     "gh_image_loss": (_i, [_i, _i, _p, _p, _p, _p, _p, _f, _f, _f, _f, _p, _p, _p, _p]),
+    "gh_project_workspace_size": (_i, [_i, C.POINTER(C.c_size_t)]),
+    "gh_project_forward": (_i, [
+        _i, _i, _i,                          # P width height
+        _p, _p, _p, _p,                      # xyz scaling rotation dirs
+        _p, _p,                              # features_dc features_rest
+        _p, _p, _p,                          # opacity label orient_conf
+        _p, _p, _p,                          # viewmatrix projmatrix campos
+        _f, _f, _f, _i, C.c_uint, _f,        # tan_fovx tan_fovy scale_modifier sh_degree flags det_eps
+        _p, _p, _p, _p, _p, _p,              # means2D colors opacities conic cov3D visible
+        _p]),                                # stream
+    "gh_project_backward": (_i, [
+        _i, _i, _i,
+        _p, _p, _p, _p,
+        _p, _p,
+        _p, _p, _p,
+        _p, _p, _p,
+        _f, _f, _f, _i, C.c_uint, _f,
+        _p,                                  # visible
+        _p,                                  # geom_buffer
+        _p, _p, _p, _p,                      # dL_dmeans2D dL_dconic dL_dcolors dL_dopacity
+        _p, _p, _p, _p, _p, _p,              # d_xyz d_scaling d_rotation d_dirs d_features_dc d_features_rest
+        _p, _p, _p, _p, _p,                  # d_opacity d_label d_orient_conf d_means2D d_camera
+        _p, _p]),                            # workspace stream
     "gh_debug_export": (_i, [_i, _i, _i, _ll, _p, _p, _p, _p, _p, _p, _p, _p, _p, _p, _p, _p]),
 }
 

@@ -256,9 +256,11 @@ int gh_backward(
     cudaStream_t stream = (cudaStream_t)stream_;
     g_err[0] = 0;
     if (P <= 0 || width <= 0 || height <= 0 || R < 0) return gh_fail(GH_E_INVALID_ARG, "gh_backward: bad sizes");
+    // conic supplied + all four 2-D gradient outputs NULL: leave the accumulation records in the geometry workspace
+    const bool keep_records = (conic_precomp != nullptr) && !dL_dmean2D && !dL_dconic && !dL_dopacity && !dL_dcolor;
     if (!background || !means3D || !colors_precomp || !viewmatrix || !projmatrix || !radii ||
-        !geom_buffer || !img_buffer || !dL_dpix || !dL_dmean2D || !dL_dconic || !dL_dopacity || !dL_dcolor ||
-        (R > 0 && !binning_buffer))
+        !geom_buffer || !img_buffer || !dL_dpix || (R > 0 && !binning_buffer) ||
+        (!keep_records && (!dL_dmean2D || !dL_dconic || !dL_dopacity || !dL_dcolor)))
         return gh_fail(GH_E_INVALID_ARG, "gh_backward: missing mandatory pointer");
     if (conic_precomp == nullptr) {
         if (!dL_dmean3D || !dL_dcov3D) return gh_fail(GH_E_INVALID_ARG, "gh_backward: dL_dmean3D/dL_dcov3D required");
@@ -270,12 +272,18 @@ int gh_backward(
     if (((size_t)colors_precomp & 7)) return gh_fail(GH_E_INVALID_ARG, "colors_precomp must be 8-byte aligned");
     if (((size_t)dL_dconic & 15)) return gh_fail(GH_E_INVALID_ARG, "dL_dconic must be 16-byte aligned");
     if (((size_t)dL_dcolor & 7)) return gh_fail(GH_E_INVALID_ARG, "dL_dcolor must be 8-byte aligned");
+    if (keep_records && (dL_dmean3D || dL_dcov3D || dL_dscale || dL_drot))
+        return gh_fail(GH_E_INVALID_ARG, "gh_backward: geometry gradients cannot be requested without the 2-D gradient outputs");
     int gx, gy; gh_grid(width, height, gx, gy);
     const int T = gx * gy;
     GhGeomWS geom = GhGeomWS::carve(geom_buffer, (size_t)P);
     GhImgWS img = GhImgWS::carve(img_buffer, (size_t)width * height, (size_t)T);
     GhBinWS bin = GhBinWS::carve(binning_buffer, (size_t)R);
 
+    if (R == 0 && keep_records) {
+        cudaError_t e = cudaMemsetAsync(geom.acc16, 0, (size_t)P * 64, stream);
+        if (e != cudaSuccess) return gh_check_cuda(e, "memset(accumulation records)");
+    }
     if (R == 0) {
         // nothing was rendered: every gradient is zero (P * floats-per-row each)
         struct { float* p; size_t n; } z[] = {{dL_dmean2D, 3}, {dL_dconic, 4}, {dL_dopacity, 1}, {dL_dcolor, GH_NUM_CHANNELS},
@@ -292,7 +300,7 @@ int gh_backward(
         if (e != cudaSuccess) return gh_check_cuda(e, "memset(accumulation records)");
         gh_launch_blend_backward(width, height, gx, gy, geom, img, bin, colors_precomp, background, dL_dpix, stream);
         g_launches += 1;
-        if (conic_precomp != nullptr) {   // otherwise the geometry backward unpacks the records itself
+        if (conic_precomp != nullptr && !keep_records) {   // otherwise the geometry backward unpacks the records itself
             gh_launch_unpack_grads(P, geom, dL_dmean2D, dL_dconic, dL_dopacity, dL_dcolor,
                                    dL_dmean3D, dL_dcov3D, dL_dscale, dL_drot, stream);
             g_launches += 1;

@@ -134,6 +134,9 @@ int gh_forward_render(
  * dL_dmean2D (P,3) [NDC units, z unused], dL_dconic (P,2,2) [.x .y .w used, .y = half the
  * off-diagonal derivative], dL_dopacity (P,1), dL_dcolor (P,C), dL_dmean3D (P,3), dL_dcov3D (P,6),
  * dL_dsh (P,M,3) [never written: SH path unreachable with C = 10], dL_dscale (P,3), dL_drot (P,4).
+ * When conic_precomp is given (nothing flows through the geometry), dL_dmean2D, dL_dconic, dL_dopacity and
+ * dL_dcolor may ALL be NULL: the blend backward's per-Gaussian accumulation records then stay in the geometry
+ * workspace for gh_project_backward to consume directly (no unpack pass).
  */
 int gh_backward(
     int P, int D, int M, int R,
@@ -234,6 +237,58 @@ int gh_allreduce_p2p(const unsigned long long* peer_bufs, const unsigned long lo
                      unsigned long long multicast_buf, int rank, int world,
                      size_t offset_floats, size_t n_floats, unsigned int epoch,
                      unsigned int* local_sync, unsigned int* nan_out, gh_stream_t stream);
+
+/*
+ * "Next" row: the caller-side projection preamble, fused.  One forward and one backward kernel
+ * replace the PyTorch code that `render()` / `render_hair()` run before every rasterizer call:
+ *   GaussianModel.get_conic / get_covariance_2d / get_covariance   src/scene/gaussian_model.py:230-315
+ *   get_mean_2d :317-337, get_depths :339-342, get_direction_2d :344-393, filter_points :143-228
+ *   the parameter activations :106-141, eval_sh (src/utils/sh_utils.py:57-112), the feature concatenation and the
+ *   boolean-mask gathers (src/gaussian_renderer/__init__.py:29-83, :122-186; strand models:
+ *   src/scene/gaussian_model_latent_strands.py:109-440).
+ * Inputs are the RAW model parameters (device float32, contiguous): xyz (P,3), scaling (P,3), rotation (P,4, raw
+ * quaternion, 16-byte aligned), dirs (P,3) or NULL, features_dc (P,1,3), features_rest (P,15,3) [NULL allowed for
+ * sh_degree 0], opacity / label / orient_conf (P,1) or NULL when their activation is a constant; viewmatrix,
+ * projmatrix (4,4, row-vector convention) and campos (3).
+ * flags: bits 0-1 scale activation (0 identity, 1 exp), 2-3 opacity (0 identity, 1 sigmoid, 2 constant 1),
+ *   4-5 label (0 identity, 1 sigmoid, 2 constant 1, 3 constant 0), 6-7 orientation confidence (0 identity, 1 exp,
+ *   3 constant 0), 8-9 direction feature (0: s_max * R[argmax s], 1: normalize(dirs), 2: zero).
+ * det_eps: added to the 2-D determinant before inversion (1e-12 GaussianModel, 1e-7 strand models).
+ * Forward outputs: means2D (P,3) NDC, colors (P,10), opacities (P,1), conic (P,3), cov3D (P,6) or NULL,
+ *   visible (P) uint8 = the caller's prefilter.  Culled Gaussians are NOT compacted away: their conic is 0, which the
+ *   rasterizer drops (zero determinant), so indices stay the model's own and `prefiltered` must be passed as 0.
+ * Backward: the incoming gradients are either the four tensors gh_backward produces (dL_dmeans2D (P,3),
+ *   dL_dconic (P,2,2) native layout, dL_dcolors (P,10), dL_dopacity (P,1)) or, when geom_buffer is given, the
+ *   accumulation records that gh_backward leaves in the geometry workspace (see gh_backward: pass NULL for its four
+ *   2-D gradient outputs).  Every row of every per-Gaussian gradient is written (zeros for culled Gaussians);
+ *   any of d_dirs, d_opacity, d_label, d_orient_conf, d_means2D may be NULL.  d_camera (device float[37], or NULL):
+ *   dL/dviewmatrix (16), dL/dprojmatrix (16), dL/dcampos (3), dL/dtan_fovx, dL/dtan_fovy -- summed per CTA and then
+ *   in a fixed order by the last CTA (deterministic); needs `workspace` (gh_project_workspace_size bytes,
+ *   16-byte aligned).
+ */
+int gh_project_workspace_size(int P, size_t* bytes);
+int gh_project_forward(
+    int P, int width, int height,
+    const float* xyz, const float* scaling, const float* rotation, const float* dirs,
+    const float* features_dc, const float* features_rest,
+    const float* opacity, const float* label, const float* orient_conf,
+    const float* viewmatrix, const float* projmatrix, const float* campos,
+    float tan_fovx, float tan_fovy, float scale_modifier, int sh_degree, unsigned int flags, float det_eps,
+    float* means2D, float* colors, float* opacities, float* conic, float* cov3D, unsigned char* visible,
+    gh_stream_t stream);
+int gh_project_backward(
+    int P, int width, int height,
+    const float* xyz, const float* scaling, const float* rotation, const float* dirs,
+    const float* features_dc, const float* features_rest,
+    const float* opacity, const float* label, const float* orient_conf,
+    const float* viewmatrix, const float* projmatrix, const float* campos,
+    float tan_fovx, float tan_fovy, float scale_modifier, int sh_degree, unsigned int flags, float det_eps,
+    const unsigned char* visible,
+    const char* geom_buffer,
+    const float* dL_dmeans2D, const float* dL_dconic, const float* dL_dcolors, const float* dL_dopacity,
+    float* d_xyz, float* d_scaling, float* d_rotation, float* d_dirs, float* d_features_dc, float* d_features_rest,
+    float* d_opacity, float* d_label, float* d_orient_conf, float* d_means2D, float* d_camera,
+    void* workspace, gh_stream_t stream);
 
 #ifdef __cplusplus
 }

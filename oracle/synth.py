@@ -299,3 +299,103 @@ def rasterizer_inputs(scene, cam, mode: str = "native", sh_degree: int = 3,
         kw = {k: (v.to(device) if isinstance(v, torch.Tensor) else v) for k, v in kw.items()}
         settings = {k: (v.to(device) if isinstance(v, torch.Tensor) else v) for k, v in settings.items()}
     return {"kwargs": kw, "settings": settings, "mask": mask}
+
+
+# ------------------------------------------------------------------------- caller preamble from RAW model parameters
+# Oracle of the fused projection op (gaussianhaircut_b200/projection.py, csrc/gh_project.cu): the whole preamble of
+# `render()` / `render_hair()` as differentiable PyTorch, from the parameters the models store.  Restates
+#   GaussianModel      scene/gaussian_model.py:106-141 (activations), :230-393, gaussian_renderer/__init__.py:29-83
+#   GaussianModelHair  scene/gaussian_model_latent_strands.py:109-148, :237-440, gaussian_renderer/__init__.py:122-186
+# and is pinned on the reference's own Python (tests/golden/pyref_project_*.npz, make_golden_pyref_project.py).
+PROJECT_GAUSSIAN_MODEL = dict(scale_act=1, opacity_act=1, label_act=1, conf_act=1, dir_mode=0, det_eps=1e-12)
+PROJECT_HAIR_MODEL = dict(scale_act=0, opacity_act=2, label_act=2, conf_act=1, dir_mode=1, det_eps=1e-7)
+
+
+def build_rotation_ref(q: torch.Tensor) -> torch.Tensor:
+    """general_utils.py:79-109: normalises q, fills the TRANSPOSED layout."""
+    q = q / torch.sqrt((q * q).sum(dim=1, keepdim=True))
+    return build_rotation_glm(q)
+
+
+def project_reference(raw: Dict[str, torch.Tensor], cam: Dict[str, object], cfg: Dict[str, object],
+                      sh_degree: int = 3, scaling_modifier: float = 1.0) -> Dict[str, torch.Tensor]:
+    """raw: xyz (P,3), scaling (P,3), rotation (P,4), f_dc (P,1,3), f_rest (P,15,3), opacity / label / conf (P,1)
+    [ignored when the activation says 'constant'], dirs (P,3) for dir_mode 1.  cam: synth.make_camera dict whose
+    matrices may be autograd leaves; 'tanfovx'/'tanfovy' may be tensors."""
+    xyz = raw["xyz"]
+    vm, pm, cc = cam["world_view_transform"].to(xyz), cam["full_proj_transform"].to(xyz), cam["camera_center"].to(xyz)
+    W, H = cam["image_width"], cam["image_height"]
+    tanx, tany = cam["tanfovx"], cam["tanfovy"]
+    s = (torch.exp(raw["scaling"]) if cfg["scale_act"] == 1 else raw["scaling"]) * scaling_modifier
+    R = build_rotation_ref(raw["rotation"])
+    M = s[:, :, None] * R
+    cov_full = M.transpose(1, 2) @ M
+    cov6 = torch.stack([cov_full[:, 0, 0], cov_full[:, 0, 1], cov_full[:, 0, 2], cov_full[:, 1, 1], cov_full[:, 1, 2],
+                        cov_full[:, 2, 2]], dim=-1)
+    fx, fy = W / (2.0 * tanx), H / (2.0 * tany)
+    t = xyz @ vm[:3, :3] + vm[3:4, :3]
+    tz = t[:, 2]
+    limx, limy = 1.3 * tanx, 1.3 * tany
+    if isinstance(limx, torch.Tensor):
+        tx = torch.maximum(torch.minimum(t[:, 0] / tz, limx), -limx) * tz
+        ty = torch.maximum(torch.minimum(t[:, 1] / tz, limy), -limy) * tz
+    else:
+        tx = torch.clamp(t[:, 0] / tz, min=-limx, max=limx) * tz
+        ty = torch.clamp(t[:, 1] / tz, min=-limy, max=limy) * tz
+    z0 = torch.zeros_like(tz)
+    J = torch.stack([torch.stack([fx / tz, z0, -(fx * tx) / (tz * tz)], dim=-1),
+                     torch.stack([z0, fy / tz, -(fy * ty) / (tz * tz)], dim=-1),
+                     torch.stack([z0, z0, z0], dim=-1)], dim=-1)
+    T = vm[None, :3, :3] @ J
+    cov2d = T.transpose(1, 2) @ cov_full.transpose(1, 2) @ T
+    a, b, c = cov2d[:, 0, 0] + 0.3, cov2d[:, 0, 1], cov2d[:, 1, 1] + 0.3
+    det = a * c - b * b
+    conic = torch.stack([c, -b, a], dim=-1) * (1.0 / (det + cfg["det_eps"]))[:, None]
+    p_hom = xyz @ pm[:3, :] + pm[3:4, :]
+    means2D = p_hom[:, :3] * (1.0 / (p_hom[:, 3:4] + 0.0000001))
+    depths = t[:, 2:3]
+    shs_view = torch.cat([raw["f_dc"], raw["f_rest"]], dim=1).transpose(1, 2)
+    d = xyz - cc[None]
+    d = d / d.norm(dim=1, keepdim=True)
+    rgb = torch.clamp_min(eval_sh(sh_degree, shs_view, d) + 0.5, 0.0)
+    if cfg["dir_mode"] == 0:
+        j = s.argmax(dim=1)                                                 # argsort(descending)[:, 0]
+        idx = torch.arange(s.shape[0], device=s.device)
+        dir3 = R[idx, j] * s[idx, j][:, None]                               # gaussian_model.py:385-389
+    elif cfg["dir_mode"] == 1:
+        dir3 = F.normalize(raw["dirs"], dim=-1)
+    else:
+        dir3 = torch.zeros_like(xyz)
+    dir2d = (dir3[:, None, :] @ T)[:, 0]
+    ones = torch.ones_like(depths)
+    act = lambda v, mode, f: f(v) if mode == 1 else (v if mode == 0 else (ones if mode == 2 else torch.zeros_like(ones)))  # noqa: E731
+    opacity = act(raw.get("opacity"), cfg["opacity_act"], torch.sigmoid)
+    label = act(raw.get("label"), cfg["label_act"], torch.sigmoid)
+    conf = act(raw.get("conf"), cfg["conf_act"], torch.exp)
+    colors = torch.cat([rgb, label, ones, dir2d, conf, depths], dim=-1)
+    with torch.no_grad():                                                   # filter_points (gaussian_model.py:143-228)
+        mask = (t[:, 2] > 0.2) & (det != 0)
+        mid = 0.5 * (a + c)
+        sq = torch.clamp(mid * mid - det, min=0.1) ** 0.5
+        radius = torch.ceil(3 * torch.maximum(mid + sq, mid - sq) ** 0.5)
+        px = ((means2D[:, 0] + 1) * W - 1.0) * 0.5
+        py = ((means2D[:, 1] + 1) * H - 1.0) * 0.5
+        gx, gy = (W + 15) // 16, (H + 15) // 16
+        x0 = torch.clamp(((px - radius) / 16).int(), 0, gx); y0 = torch.clamp(((py - radius) / 16).int(), 0, gy)
+        x1 = torch.clamp(((px + radius + 15) / 16).int(), 0, gx); y1 = torch.clamp(((py + radius + 15) / 16).int(), 0, gy)
+        mask = mask & ((x1 - x0) * (y1 - y0) != 0)
+    return {"means2D": means2D, "conic": conic, "colors": colors, "opacity": opacity, "cov3D": cov6, "mask": mask,
+            "cov2d": torch.stack([a, b, c], dim=-1)}
+
+
+def raw_params_from_scene(scene: Dict[str, torch.Tensor], flavour: str = "gaussian_model") -> Dict[str, torch.Tensor]:
+    """The parameters a model would store for a synthetic scene (logit / log spaces for GaussianModel)."""
+    logit = lambda p: torch.log(p / (1 - p))   # noqa: E731
+    if flavour == "gaussian_model":
+        return {"xyz": scene["xyz"].clone(), "scaling": torch.log(scene["scaling"]), "rotation": scene["rotation"].clone(),
+                "f_dc": scene["f_dc"].clone(), "f_rest": scene["f_rest"].clone(),
+                "opacity": logit(scene["opacity"].clamp(1e-6, 1 - 1e-6)), "label": logit(scene["label"].clamp(1e-6, 1 - 1e-6)),
+                "conf": torch.log(scene["orient_conf"])}
+    return {"xyz": scene["xyz"].clone(), "scaling": scene["scaling"].clone(), "rotation": scene["rotation"].clone(),
+            "dirs": scene["dir"].clone(), "f_dc": scene["f_dc"].clone(), "f_rest": scene["f_rest"].clone(),
+            "conf": torch.log(scene["orient_conf"])}
