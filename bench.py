@@ -636,6 +636,84 @@ def main():
                                          else "PyTorch restatement of the reference's loss_utils + autograd (oracle/loss_oracle.py)"}
         log(f"[bench] iteration (fwd + losses + bwd + Adam): {ms_iter:.3f} ms/step; image losses alone {ms_loss:.3f} ms")
 
+    # ---------------------------------------------------------------- fourth figure: a train_gaussians.py iteration from RAW model parameters
+    # What src/train_gaussians.py:96-181 runs per iteration: render(cam, gaussians) -- i.e. the model-side projection
+    # preamble + the rasterizer -- then the image losses, backward and the optimizer step over
+    # the model's 8 parameter tensors.  mine: renderer.render_raw (fused projection + rasterizer, one autograd node) ->
+    # losses.hair_image_loss -> backward -> FusedAdam.  reference: the reference's OWN render() imported unmodified
+    # (oracle/ref_python.py) on its own rasterizer build -> the PyTorch losses of its trainer -> torch.optim.Adam with the
+    # trainer's per-parameter NaN host syncs.
+    train_full = None
+    if args.mode == "native" and not use_dist and rank == 0:
+        import types
+        import ref_python
+        gen = torch.Generator(device="cpu").manual_seed(11)
+        gt_image = torch.rand(3, H, W, generator=gen).to(device)
+        gt_mask = ((torch.rand(2, H, W, generator=gen) > 0.3).float() * (0.5 + 0.5 * torch.rand(2, H, W, generator=gen))).to(device)
+        gt_angle = torch.rand(1, H, W, generator=gen).to(device)
+        gt_conf = torch.rand(1, H, W, generator=gen).to(device)
+        lambdas = (0.8, 0.2, 0.1, 0.1)
+        raw = synth.raw_params_from_scene(scene, "gaussian_model")
+        cam_d = synth.make_camera(0, W, H)
+        cam_ns = ref_python.make_camera(cam_d, device)
+        bg_t = torch.tensor(synth.BG_DEFAULT, device=device)
+        pnames = ("_xyz", "_features_dc", "_features_rest", "_opacity", "_label", "_scaling", "_rotation", "_orient_conf")
+        keys = ("xyz", "f_dc", "f_rest", "opacity", "label", "scaling", "rotation", "conf")
+        lrs8 = (1e-9,) * 8          # negligible updates: the workload (R, splat sizes) stays the one being measured
+        how = None
+        if args.impl == "mine":
+            from gaussianhaircut_b200 import renderer, losses as ghl
+            from gaussianhaircut_b200.optim import FusedAdam
+            pc = types.SimpleNamespace(active_sh_degree=3, max_sh_degree=3)
+            for n, k in zip(pnames, keys):
+                setattr(pc, n, torch.nn.Parameter(raw[k].to(device).contiguous()))
+            opt8 = FusedAdam([{"params": [getattr(pc, n)], "lr": lr, "name": n} for n, lr in zip(pnames, lrs8)], eps=1e-15)
+            pipe_ns = types.SimpleNamespace(debug=False)
+
+            def full_iter(i):
+                renders, radii, viewspace = renderer.render_raw(cam_ns, pc, pipe_ns, bg_t)
+                loss, _parts = ghl.hair_image_loss(renders, gt_image, gt_mask, gt_angle, gt_conf, *lambdas)
+                loss.backward()
+                opt8.step()
+                opt8.zero_grad(set_to_none=True)
+                last["loss"] = loss
+            how = "renderer.render_raw (gh_project_forward/backward + rasterizer) -> gh_image_loss -> FusedAdam (8 tensors)"
+        elif ref_python.available():
+            gr = ref_python.load_renderer("ref")
+            import utils.loss_utils as loss_oracle        # the reference's own loss functions (src/utils/loss_utils.py), unmodified
+            pc = ref_python.make_gaussian_model(scene, device)
+            plist8 = [getattr(pc, n) for n in pnames]
+            opt8 = torch.optim.Adam([{"params": [p], "lr": lr, "name": n} for p, n, lr in zip(plist8, pnames, lrs8)], lr=0.0, eps=1e-15)
+            pipe_ns = ref_python.pipe()
+
+            def full_iter(i):
+                pkg = gr.render(cam_ns, pc, pipe_ns, bg_t)
+                # the trainer's loss (train_gaussians.py:126-140) on the maps render() returns
+                Ll1 = loss_oracle.l1_loss(pkg["render"], gt_image, mask=gt_mask[1:].detach())
+                Lssim = 1.0 - loss_oracle.ssim(pkg["render"] * gt_mask[1:], gt_image * gt_mask[1:])
+                Lmask = loss_oracle.l1_loss(pkg["mask"], gt_mask)
+                Lor = loss_oracle.or_loss(pkg["orient_angle"], gt_angle, pkg["orient_conf"], weight=torch.ones_like(gt_mask[:1]) * gt_conf, mask=gt_mask[:1])
+                if torch.isnan(Lor).any():
+                    Lor = torch.zeros_like(Ll1)
+                loss = Ll1 * lambdas[0] + Lssim * lambdas[1] + Lmask * lambdas[2] + Lor * lambdas[3]
+                loss.backward()
+                with torch.no_grad():
+                    for p8 in plist8[:7]:
+                        if p8.grad is not None and p8.grad.isnan().any():
+                            opt8.zero_grad(set_to_none=True)
+                    opt8.step()
+                    opt8.zero_grad(set_to_none=True)
+                last["loss"] = loss
+            how = ("the reference's own render() (src/gaussian_renderer/__init__.py:23, imported unmodified) on its own rasterizer build -> "
+                   "PyTorch losses of its trainer -> torch.optim.Adam + NaN host syncs")
+        if how is not None:
+            for i in range(3):
+                full_iter(i)
+            ms_full = timed(max(5, args.steps // 2), full_iter) / max(5, args.steps // 2)
+            train_full = {"ms_per_step": ms_full, "value": P_total / (ms_full * 1e-3), "unit": UNIT, "how": how,
+                          "parameters": list(pnames), "loss": float(last["loss"].detach())}
+            log(f"[bench] train_gaussians.py iteration from raw parameters: {ms_full:.3f} ms/step (loss {train_full['loss']:.5f})")
+
     if args.impl == "reference":
         cpu_baseline = {"value": value, "unit": UNIT, "cores": sm_count, "kind": "reference",
                         "sample": f"{args.steps} steps of the same workload; the reference's own CUDA extension "
@@ -662,6 +740,7 @@ def main():
             "call_shapes": call_shapes,
             "with_adam": with_adam,
             "train_iteration": train_iter,
+            "train_iteration_full": train_full,
             "cpu_baseline": cpu_baseline,
         }
         if args.impl == "reference":

@@ -208,6 +208,34 @@ def rasterize_gaussians_backward_arena(
     return flat, g, dL_dsh
 
 
+def rasterize_gaussians_backward_records(background, means3D, radii, colors, conic_precomp, viewmatrix, projmatrix,
+                                         tan_fovx, tan_fovy, dL_dout_color, campos, geomBuffer, R, binningBuffer,
+                                         imageBuffer, debug) -> None:
+    """Blend backward only, for the conic_precomp call shape: the per-Gaussian accumulation records (dL/d colour,
+    2-D mean, conic, opacity) are LEFT in `geomBuffer` for `gh_project_backward` to consume directly -- no unpack
+    pass, no intermediate gradient tensors (projection.project_backward(geom_buffer=...))."""
+    lib = _capi.load()
+    device = means3D.device
+    P = int(means3D.size(0))
+    if P == 0:
+        return
+    H, W = int(dL_dout_color.size(1)), int(dL_dout_color.size(2))
+    if conic_precomp is None or conic_precomp.numel() == 0:
+        raise RuntimeError("rasterize_gaussians_backward_records needs the conic_precomp call shape")
+    with torch.cuda.device(device):
+        dL = _prep(dL_dout_color, "dL_dout_color", device)
+        _capi.check(lib.gh_backward(
+            P, 0, 0, int(R), W, H,
+            _ptr(background), _ptr(means3D), None, _ptr(colors),
+            None, 1.0, None, None, _ptr(conic_precomp),
+            _ptr(viewmatrix), _ptr(projmatrix), _ptr(campos),
+            float(tan_fovx), float(tan_fovy), _ptr(radii),
+            _ptr(geomBuffer), _ptr(binningBuffer), _ptr(imageBuffer),
+            _ptr(dL),
+            None, None, None, None, None, None, None, None, None,
+            int(bool(debug)), _stream(device)))
+
+
 def rasterize_gaussians_backward(
     background: torch.Tensor, means3D: torch.Tensor, radii: torch.Tensor, colors: torch.Tensor,
     scales: torch.Tensor, rotations: torch.Tensor, scale_modifier: float,

@@ -105,16 +105,27 @@ def _common_args(pi: ProjectionInputs):
             pi.tanx, pi.tany, pi.mod, pi.sh_degree, pi.flags, pi.det_eps)
 
 
-def project_forward(pi: ProjectionInputs, want_cov3D: bool = False, means2D_out: Optional[torch.Tensor] = None):
+def alloc_outputs(P: int, dev: torch.device, want_cov3D: bool = False, means2D_out: Optional[torch.Tensor] = None):
+    f = dict(dtype=torch.float32, device=dev)
+    return {"means2D": means2D_out if means2D_out is not None else torch.empty((P, 3), **f),
+            "colors": torch.empty((P, 10), **f), "opacity": torch.empty((P, 1), **f), "conic": torch.empty((P, 3), **f),
+            "visible": torch.empty((P,), dtype=torch.uint8, device=dev),
+            "cov3D": torch.empty((P, 6), **f) if want_cov3D else None}
+
+
+def project_forward(pi: ProjectionInputs, want_cov3D: bool = False, means2D_out: Optional[torch.Tensor] = None,
+                    out: Optional[Dict[str, torch.Tensor]] = None):
     """-> dict(means2D (P,3) NDC, colors (P,10), opacity (P,1), conic (P,3) [zeros where culled], visible (P) uint8,
-    cov3D (P,6) or None).  `means2D_out`: write the NDC means into this (P,3) float32 tensor instead of allocating."""
+    cov3D (P,6) or None).  `means2D_out`: write the NDC means into this (P,3) float32 tensor instead of allocating;
+    `out`: write everything into these preallocated tensors (e.g. row slices of larger buffers)."""
     lib = _capi.load()
     dev, P = pi.device, pi.P
-    f = dict(dtype=torch.float32, device=dev)
-    out = {"means2D": means2D_out if means2D_out is not None else torch.empty((P, 3), **f),
-           "colors": torch.empty((P, 10), **f), "opacity": torch.empty((P, 1), **f), "conic": torch.empty((P, 3), **f),
-           "visible": torch.empty((P,), dtype=torch.uint8, device=dev),
-           "cov3D": torch.empty((P, 6), **f) if want_cov3D else None}
+    if out is None:
+        out = alloc_outputs(P, dev, want_cov3D, means2D_out)
+    else:
+        for k, v in out.items():
+            if v is not None and (not v.is_contiguous() or v.shape[0] != P):
+                raise RuntimeError(f"projection: preallocated output '{k}' must be contiguous with {P} rows")
     if P == 0:
         return out
     with torch.cuda.device(dev):

@@ -1,0 +1,211 @@
+"""GPU tests of the fused projection preamble ("next" row 8f-1) and of the `render()` / `render_hair()` drop-ins built
+on it (gaussianhaircut_b200/projection.py, renderer.py):
+
+* the two kernels against PyTorch autograd of the restated preamble (oracle/synth.py `project_reference`, pinned on
+  the reference's Python by tests/test_project_cpu.py) at 500k Gaussians: values, every parameter gradient and the
+  camera gradients (view / projection matrix, camera centre, tan fov), in both incoming-gradient modes;
+* `renderer.render` / `renderer.render_hair` against the reference's OWN functions imported unmodified and running
+  on the reference's OWN rasterizer build (oracle/ref_python.py + oracle/_ref): everything a trainer reads back.
+Tolerance: the north-star 1e-4 (norm-relative) on maps and gradients."""
+import os
+import sys
+
+import pytest
+import torch
+
+import _util
+from _util import rel_err
+
+pytestmark = pytest.mark.gpu
+REL_TOL = 1e-4
+
+sys.path.insert(0, os.path.join(_util.ROOT, "oracle"))
+import ref_python  # noqa: E402
+
+
+def _leaves(raw, dev):
+    return {k: v.clone().to(dev).requires_grad_(True) for k, v in raw.items()}
+
+
+@pytest.mark.parametrize("flavour,strands,W,H,deg", [("gaussian_model", 5000, 1920, 1080, 3), ("hair", 5000, 1920, 1080, 3),
+                                                     ("gaussian_model", 37, 250, 187, 1), ("gaussian_model", 37, 250, 187, 0)])
+def test_projection_kernels_match_autograd(cuda_device, flavour, strands, W, H, deg):
+    from gaussianhaircut_b200 import projection
+    synth = _util.synth
+    dev = cuda_device
+    scene = synth.make_strand_scene(strands, seed=2)
+    cam = dict(synth.make_camera(19, W, H))
+    cfg = dict(synth.PROJECT_GAUSSIAN_MODEL if flavour == "gaussian_model" else synth.PROJECT_HAIR_MODEL)
+    raw = synth.raw_params_from_scene(scene, flavour)
+    if flavour == "gaussian_model":
+        raw["rotation"] = raw["rotation"] * (0.5 + torch.rand(raw["rotation"].shape[0], 1, generator=torch.Generator().manual_seed(1)))
+    leaves = _leaves(raw, dev)
+    camg = dict(cam)
+    for k in ("world_view_transform", "full_proj_transform", "camera_center"):
+        camg[k] = cam[k].to(dev).requires_grad_(True)
+    camg["tanfovx"] = torch.tensor(cam["tanfovx"], dtype=torch.float32, device=dev, requires_grad=True)
+    camg["tanfovy"] = torch.tensor(cam["tanfovy"], dtype=torch.float32, device=dev, requires_grad=True)
+    ref = synth.project_reference(leaves, camg, cfg, sh_degree=deg)
+    mask = ref["mask"]
+
+    pi = projection.pack_inputs(leaves["xyz"], leaves["scaling"], leaves["rotation"], leaves.get("dirs"), leaves["f_dc"],
+                                leaves["f_rest"], leaves.get("opacity"), leaves.get("label"), leaves.get("conf"),
+                                camg["world_view_transform"], camg["full_proj_transform"], camg["camera_center"],
+                                cam["tanfovx"], cam["tanfovy"], W, H, deg, 1.0, cfg)
+    out = projection.project_forward(pi, want_cov3D=True)
+    torch.cuda.synchronize()
+    flips = int((out["visible"].bool() != mask).sum())
+    assert flips <= max(2, mask.numel() // 100000), f"{flips} prefilter decisions differ"       # image-border ties only
+    both = out["visible"].bool() & mask
+    assert rel_err(out["means2D"], ref["means2D"]) <= 1e-5
+    assert rel_err(out["conic"][both], ref["conic"][both]) <= REL_TOL
+    assert float(out["conic"][~out["visible"].bool()].abs().sum()) == 0.0
+    assert rel_err(out["colors"], ref["colors"]) <= 1e-5
+    assert rel_err(out["opacity"], ref["opacity"]) <= 1e-6
+    assert rel_err(out["cov3D"], ref["cov3D"]) <= 1e-5
+
+    g = torch.Generator().manual_seed(3)
+    gin = {"means2D": torch.randn(ref["means2D"].shape, generator=g).to(dev), "conic": (torch.randn(ref["conic"].shape, generator=g) * 1e-3).to(dev),
+           "colors": torch.randn(ref["colors"].shape, generator=g).to(dev), "opacity": torch.randn(ref["opacity"].shape, generator=g).to(dev)}
+    gin["means2D"][:, 2] = 0.0
+    m = out["visible"].bool()[:, None].float()          # gradients reach exactly the Gaussians the op kept
+    loss = sum((ref[k] * gin[k] * m).sum() for k in gin)
+    loss.backward()
+    # the rasterizer's native conic-gradient layout: (P,2,2) with HALF the off-diagonal derivative at [0][1]
+    conic4 = torch.zeros(mask.numel(), 2, 2, device=dev)
+    conic4[:, 0, 0] = gin["conic"][:, 0]; conic4[:, 0, 1] = 0.5 * gin["conic"][:, 1]; conic4[:, 1, 1] = gin["conic"][:, 2]
+    d = projection.project_backward(pi, out["visible"], dL_dmeans2D=gin["means2D"], dL_dconic4=conic4, dL_dcolors=gin["colors"],
+                                    dL_dopacity=gin["opacity"], camera_grads=True, want_means2D_grad=True)
+    torch.cuda.synchronize()
+    names = {"xyz": "xyz", "scaling": "scaling", "rotation": "rotation", "f_dc": "f_dc", "f_rest": "f_rest", "conf": "conf"}
+    names.update({"opacity": "opacity", "label": "label"} if flavour == "gaussian_model" else {"dirs": "dirs"})
+    for k, src in names.items():
+        gref = leaves[src].grad
+        if gref is None:
+            gref = torch.zeros_like(leaves[src])
+        e = rel_err(d[k].reshape(gref.shape), gref)
+        assert e <= REL_TOL, f"{k}: {e}"
+    assert rel_err(d["viewmatrix"], camg["world_view_transform"].grad) <= REL_TOL
+    assert rel_err(d["projmatrix"], camg["full_proj_transform"].grad) <= REL_TOL
+    if deg > 0:
+        assert rel_err(d["campos"], camg["camera_center"].grad) <= REL_TOL
+    else:
+        assert float(d["campos"].abs().max()) == 0.0
+    gt = torch.stack([camg["tanfovx"].grad, camg["tanfovy"].grad])
+    assert rel_err(d["tanfov"], gt) <= REL_TOL
+    assert torch.equal(d["means2D"][:, :2], (gin["means2D"] * m)[:, :2])
+    # deterministic camera reduction
+    d2 = projection.project_backward(pi, out["visible"], dL_dmeans2D=gin["means2D"], dL_dconic4=conic4, dL_dcolors=gin["colors"],
+                                     dL_dopacity=gin["opacity"], camera_grads=True)
+    assert torch.equal(d2["viewmatrix"], d["viewmatrix"]) and torch.equal(d2["projmatrix"], d["projmatrix"])
+
+
+def _weights(H, W, device, seed):
+    g = torch.Generator().manual_seed(seed)
+    return {k: torch.rand(c, H, W, generator=g).to(device) for k, c in (("render", 3), ("mask", 2), ("orient_angle", 1), ("orient_conf", 1))}
+
+
+def _loss(pkg, Wt):
+    return sum((pkg[k] * Wt[k]).sum() for k in Wt)
+
+
+def _need_reference():
+    if not ref_python.available() or not _util.ref_available():
+        pytest.skip("reference Python sources / oracle/_ref not staged")
+
+
+@pytest.mark.parametrize("strands,W,H", [(300, 512, 384), (5000, 1920, 1080)], ids=["30k-512x384", "500k-1080p"])
+def test_fused_render_matches_the_reference_pipeline(cuda_device, strands, W, H):
+    """renderer.render (fused projection + this repository's rasterizer) against the reference's render() running
+    on the reference's rasterizer: the whole reference pipeline, nothing of the product in it."""
+    _need_reference()
+    from gaussianhaircut_b200 import renderer
+    synth = _util.synth
+    scene = synth.make_strand_scene(strands, seed=3)
+    g = torch.Generator().manual_seed(4)
+    scene["rotation"] = scene["rotation"] * (0.6 + 0.8 * torch.rand(scene["rotation"].shape[0], 1, generator=g))
+    scene["scaling"] = scene["scaling"] * torch.tensor([1.0, 1.0, 1.5])        # three distinct scales: unambiguous arg-max
+    cam_d = synth.make_camera(11, W, H)
+    bg = torch.tensor(synth.BG_DEFAULT, device=cuda_device)
+    Wt = _weights(H, W, cuda_device, 5)
+    ref_mod = ref_python.load_renderer("ref")
+    res = {}
+    for which, fn in (("mine", renderer.render), ("ref", ref_mod.render)):
+        pc = ref_python.make_gaussian_model(scene, cuda_device)
+        cam = ref_python.make_camera(cam_d, cuda_device, trainable=True)
+        pkg = fn(cam, pc, ref_python.pipe(), bg)
+        _loss(pkg, Wt).backward()
+        torch.cuda.synchronize()
+        res[which] = (pkg, pc, cam)
+    (pa, ma, ca), (pb, mb, cb) = res["mine"], res["ref"]
+    vis_a, vis_b = pa["visibility_filter"], pb["visibility_filter"]
+    assert int((vis_a != vis_b).sum()) <= max(2, vis_b.numel() // 100000)
+    assert int((pa["radii"] != pb["radii"]).sum()) <= max(4, vis_b.numel() // 20000)    # ceil() of a radius computed two ways
+    for k in ("render", "mask", "orient_conf"):
+        assert rel_err(pa[k], pb[k]) <= REL_TOL, f"{k}: {rel_err(pa[k], pb[k])}"
+    assert rel_err(pa["orient_angle"], pb["orient_angle"]) <= 1e-3
+    assert rel_err(pa["viewspace_points"].detach(), pb["viewspace_points"].detach()) <= 1e-5
+    for name in ref_python.MODEL_PARAMS:
+        ga, gb = getattr(ma, name).grad, getattr(mb, name).grad
+        assert ga is not None and gb is not None, name
+        assert rel_err(ga, gb) <= 2 * REL_TOL, f"{name}: {rel_err(ga, gb)}"
+    for name in ("world_view_transform", "full_proj_transform", "camera_center"):
+        assert rel_err(getattr(ca, name).grad, getattr(cb, name).grad) <= 2 * REL_TOL, f"camera {name}: {rel_err(getattr(ca, name).grad, getattr(cb, name).grad)}"
+    assert rel_err(pa["viewspace_points"].grad, pb["viewspace_points"].grad) <= 2 * REL_TOL
+
+
+def test_fused_render_hair_matches_the_reference_pipeline(cuda_device):
+    _need_reference()
+    from gaussianhaircut_b200 import renderer
+    synth = _util.synth
+    W, H = 512, 512
+    head = synth.make_blob_scene(20000, seed=2, spread=0.08, max_scale=0.004)
+    hair = synth.make_strand_scene(500, seed=4, opacity_mode="ones")
+    cam_d = synth.make_camera(7, W, H)
+    bg = torch.tensor(synth.BG_DEFAULT, device=cuda_device)
+    Wt = _weights(H, W, cuda_device, 9)
+    ref_mod = ref_python.load_renderer("ref")
+    res = {}
+    for which, fn in (("mine", renderer.render_hair), ("ref", ref_mod.render_hair)):
+        pc, pc_hair = ref_python.make_hair_models(head, hair, cuda_device)
+        cam = ref_python.make_camera(cam_d, cuda_device, trainable=True)
+        pkg = fn(cam, pc, pc_hair, ref_python.pipe(), bg)
+        _loss(pkg, Wt).backward()
+        torch.cuda.synchronize()
+        res[which] = (pkg, pc_hair, cam)
+    (pa, ha, ca), (pb, hb, cb) = res["mine"], res["ref"]
+    assert int((pa["visibility_filter"] != pb["visibility_filter"]).sum()) <= 2
+    for k in ("render", "mask", "orient_conf"):
+        assert rel_err(pa[k], pb[k]) <= REL_TOL, f"{k}: {rel_err(pa[k], pb[k])}"
+    assert rel_err(pa["orient_angle"], pb["orient_angle"]) <= 1e-3
+    for name in ref_python.HAIR_PARAMS:
+        ga, gb = getattr(ha, name).grad, getattr(hb, name).grad
+        assert ga is not None and gb is not None, name
+        assert rel_err(ga, gb) <= 2 * REL_TOL, f"{name}: {rel_err(ga, gb)}"
+    for name in ("world_view_transform", "full_proj_transform", "camera_center"):
+        assert rel_err(getattr(ca, name).grad, getattr(cb, name).grad) <= 2 * REL_TOL, name
+    assert rel_err(pa["viewspace_points"].grad, pb["viewspace_points"].grad) <= 2 * REL_TOL
+
+
+def test_projection_api_errors(cuda_device):
+    from gaussianhaircut_b200 import projection
+    synth = _util.synth
+    scene = synth.make_strand_scene(2, seed=0)
+    raw = synth.raw_params_from_scene(scene, "gaussian_model")
+    cam = synth.make_camera(0, 64, 48)
+    args = lambda r, dev: (r["xyz"].to(dev), r["scaling"].to(dev), r["rotation"].to(dev), None, r["f_dc"].to(dev), r["f_rest"].to(dev),  # noqa: E731
+                           r["opacity"].to(dev), r["label"].to(dev), r["conf"].to(dev), cam["world_view_transform"].to(dev),
+                           cam["full_proj_transform"].to(dev), cam["camera_center"].to(dev), cam["tanfovx"], cam["tanfovy"], 64, 48, 3, 1.0,
+                           projection.GAUSSIAN_MODEL)
+    with pytest.raises(RuntimeError, match="no CPU path"):
+        projection.pack_inputs(*args(raw, "cpu"))
+    bad = dict(raw, xyz=raw["xyz"].reshape(-1))
+    with pytest.raises(RuntimeError, match="means3D must have dimensions"):
+        projection.pack_inputs(*args(bad, cuda_device))
+    bad = dict(raw, f_rest=raw["f_rest"][:, :8])
+    with pytest.raises(RuntimeError, match="features_rest"):
+        projection.pack_inputs(*args(bad, cuda_device))
+    pi = projection.pack_inputs(*args(raw, cuda_device))
+    pi.sh_degree = 4
+    with pytest.raises(RuntimeError, match="sh_degree must be 0..3"):
+        projection.project_forward(pi)
