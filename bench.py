@@ -56,6 +56,7 @@ def parse_args():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-roofline", action="store_true")
     ap.add_argument("--ref-steps", type=int, default=10)
+    ap.add_argument("--repeats", type=int, default=5, help="how many times the timed K-step window is repeated (median reported)")
     ap.add_argument("--collective", default="auto", choices=["auto", "peer-mc", "peer-nomc", "nccl"],
                     help="N>1: gh_allreduce_p2p over symmetric memory (auto: peer ld/st up to 4 GPUs, NVLS multimem from 8) or NCCL")
     return ap.parse_args()
@@ -310,11 +311,16 @@ def main():
     sampler = ClockSampler(local_rank)
     if rank == 0:
         sampler.start()
-    ms_total = timed(args.steps, step)
-    clocks = sampler.stop() if rank == 0 else None
+    # the K-step window is timed `--repeats` times back to back (each bracketed by barrier + synchronize, max over
+    # ranks) and the MEDIAN window is reported; every window is listed in `ms_per_step_repeats`
+    windows = []
     gpu_launches = None
-    if args.impl == "mine":
-        gpu_launches = int(_capi.load().gh_kernel_launch_count() - launches0)
+    for rep in range(max(1, args.repeats)):
+        windows.append(timed(args.steps, step))
+        if rep == 0 and args.impl == "mine":
+            gpu_launches = int(_capi.load().gh_kernel_launch_count() - launches0)
+    clocks = sampler.stop() if rank == 0 else None
+    ms_total = statistics.median(windows)
     ms_per_step = ms_total / args.steps
     n_eff = N if args.impl == "mine" else 1       # reference arm: rank 0 alone runs (one GPU's worth of work)
     value = (args.steps * P * n_eff) / (ms_total * 1e-3)
@@ -342,41 +348,69 @@ def main():
         last["R"] = int(R_mean)
 
     # ---------------------------------------------------------------- end to end through the public API
+    # One step = what a trainer does around the op for one view (src/train_gaussians.py:103-140), through the public
+    # Python API: the view's camera and its SUPERVISION MAPS arrive from pinned host memory in the dtypes the dataset
+    # stores them in (image 3 + masks 2 + orientation angle 1 planes of uint8 -- they are 8-bit PNGs,
+    # src/utils/camera_utils.py:53-66 -- and the float32 orientation confidence), are widened on the device,
+    # GaussianRasterizer(settings)(**tensors) renders, the trainer's image loss (L1 + SSIM + mask + orientation) is
+    # evaluated on the render, loss.backward() runs the rasterizer backward, and loss.item() comes back to the host.
+    # mine: gaussianhaircut_b200.losses.hair_image_loss (fused kernels); reference arm: the same harness with the
+    # reference rasterizer build and the PyTorch loss functions its trainer runs.  At N > 1 the gradients of the op are
+    # summed with ONE gh_allreduce_p2p over the arena the backward wrote into (rasterizer.set_gradient_arena).
     e2e = None
     if not args.no_e2e:
         mod = pkg
+        gen = torch.Generator(device="cpu").manual_seed(77)
         host_views = []
         for inp in views:
             s = inp["settings"]
             host_views.append({
                 "view": s["viewmatrix"].cpu().pin_memory(), "proj": s["projmatrix"].cpu().pin_memory(),
                 "campos": s["campos"].cpu().pin_memory(),
+                # 8-bit maps as the dataset stores them + float32 confidence
+                "u8": torch.randint(0, 256, (6, H, W), dtype=torch.uint8, generator=gen).pin_memory(),
+                "conf": torch.rand(1, H, W, generator=gen).pin_memory(),
             })
-        Wt_host = dL.cpu().pin_memory()
         params = []
         for inp in views:
             kw = {k: (v.detach().clone().requires_grad_(True) if isinstance(v, torch.Tensor) else v)
                   for k, v in inp["kwargs"].items()}
             params.append(kw)
-        h2d = Wt_host.numel() * 4 + sum(t.numel() * 4 for t in host_views[0].values())
+        h2d = sum(t.numel() * t.element_size() for t in host_views[0].values())
+        lambdas = (0.8, 0.2, 0.1, 0.1)      # lambda_dl1, lambda_dssim, lambda_dmask, lambda_dorient (arguments/__init__.py defaults' order)
+        if args.impl == "mine":
+            from gaussianhaircut_b200 import losses as ghl
+            from gaussianhaircut_b200 import rasterizer as ghr
 
-        # A data loader feeds the step: the NEXT step's per-view inputs (camera + supervision tensor) are
-        # copied host->device on a side stream into one of two device slots while the current step
-        # computes (same harness for both arms); every copy of every step lies inside the timed region.
+            def image_loss(color, gi, gm, ga, gc):
+                return ghl.hair_image_loss(color, gi, gm, ga, gc, *lambdas)[0]
+            if par is not None:
+                ghr.set_gradient_arena(par.buffer)
+        else:
+            import loss_oracle
+
+            def image_loss(color, gi, gm, ga, gc):
+                return loss_oracle.training_loss(color, gi, gm, ga, gc, *lambdas)[0]
+
+        # A data loader feeds the step: the NEXT step's per-view inputs are copied host->device on a side stream into
+        # one of two device slots while the current step computes (same harness for both arms); every copy of every
+        # step lies inside the timed region.
         copy_stream = torch.cuda.Stream(device=device)
-        slots = [{"Wt": torch.empty_like(dL), "view": torch.empty(4, 4, device=device), "proj": torch.empty(4, 4, device=device),
+        slots = [{"u8": torch.empty((6, H, W), dtype=torch.uint8, device=device), "conf": torch.empty((1, H, W), device=device),
+                  "view": torch.empty(4, 4, device=device), "proj": torch.empty(4, 4, device=device),
                   "campos": torch.empty(3, device=device), "ready": torch.cuda.Event(), "free": torch.cuda.Event()} for _ in range(2)]
         for sl in slots:
             sl["free"].record(torch.cuda.current_stream(device))
+
+        def copy_in(sl, hv):
+            for k in ("u8", "conf", "view", "proj", "campos"):
+                sl[k].copy_(hv[k], non_blocking=True)
 
         def prefetch(i):
             sl, hv = slots[i % 2], host_views[i % len(views)]
             with torch.cuda.stream(copy_stream):
                 copy_stream.wait_event(sl["free"])                # the step that last used this slot is done
-                sl["Wt"].copy_(Wt_host, non_blocking=True)
-                sl["view"].copy_(hv["view"], non_blocking=True)
-                sl["proj"].copy_(hv["proj"], non_blocking=True)
-                sl["campos"].copy_(hv["campos"], non_blocking=True)
+                copy_in(sl, hv)
                 sl["ready"].record(copy_stream)
 
         e2e_state = {"next": 0, "overlap": True}
@@ -394,11 +428,7 @@ def main():
                 prefetch(i + 1)                                   # overlaps with this step's compute
                 e2e_state["next"] = i + 2
             else:                                                 # serial loader: copy, then compute, on one stream
-                hv = host_views[j]
-                sl["Wt"].copy_(Wt_host, non_blocking=True)
-                sl["view"].copy_(hv["view"], non_blocking=True)
-                sl["proj"].copy_(hv["proj"], non_blocking=True)
-                sl["campos"].copy_(hv["campos"], non_blocking=True)
+                copy_in(sl, host_views[j])
             settings = mod.GaussianRasterizationSettings(
                 image_height=s["image_height"], image_width=s["image_width"], tanfovx=s["tanfovx"],
                 tanfovy=s["tanfovy"], bg=s["bg"], scale_modifier=1.0, viewmatrix=sl["view"], projmatrix=sl["proj"],
@@ -408,14 +438,19 @@ def main():
             for v in kw.values():
                 if isinstance(v, torch.Tensor):
                     v.grad = None
+            # widen the 8-bit maps on the device (what `PILtoTorch(...)/255` did once on the host in the reference loader)
+            maps = sl["u8"].float().mul_(1.0 / 255.0)
             color, _radii = rast(**kw)
-            loss = (color * sl["Wt"]).sum()
+            loss = image_loss(color, maps[0:3], maps[3:5], maps[5:6], sl["conf"])
             loss.backward()
             sl["free"].record(cur)
             if use_dist:
-                for v in kw.values():
-                    if isinstance(v, torch.Tensor) and v.grad is not None:
-                        dist.all_reduce(v.grad, op=dist.ReduceOp.SUM)
+                if par is not None:
+                    par.all_reduce(n_floats=native.trainable_floats(P) if args.mode == "native" else native.arena_floats(P))
+                else:
+                    for v in kw.values():
+                        if isinstance(v, torch.Tensor) and v.grad is not None:
+                            dist.all_reduce(v.grad, op=dist.ReduceOp.SUM)
             last["loss"] = float(loss.item())          # device -> host read of the step's result
 
         # warm-up must visit every cycled view once: workspace sizes depend on the view (R varies), and a
@@ -436,18 +471,23 @@ def main():
                 e2e_step(i)
             torch.cuda.synchronize(); copy_stream.synchronize()
             e2e_state["next"] = 0
-            results[overlap] = timed(e2e_steps, e2e_step)
+            reps = [timed(e2e_steps, e2e_step) for _ in range(3)]
+            results[overlap] = statistics.median(reps)
             copy_stream.synchronize()
+        if args.impl == "mine" and par is not None:
+            ghr.set_gradient_arena(None)
         best_overlap = min(results, key=results.get)
         ms_e2e = results[best_overlap]
         e2e_value = (e2e_steps * P * n_eff) / (ms_e2e * 1e-3)
         e2e = {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": 4,
-               "ms_per_step": ms_e2e / e2e_steps, "steps": e2e_steps,
+               "ms_per_step": ms_e2e / e2e_steps, "steps": e2e_steps, "repeats": 3,
                "loader": "prefetch on a copy stream" if best_overlap else "serial copy on the compute stream",
                "ms_per_step_prefetch": results[True] / e2e_steps, "ms_per_step_serial": results[False] / e2e_steps,
-               "api": "GaussianRasterizer(...)(**tensors) + autograd backward; every step copies its camera + (10,H,W) "
-                      "supervision tensor from pinned host memory (double-buffered on a copy stream, overlapping the "
-                      "previous step's compute) and reads loss.item() back"}
+               "image_loss": "gh_image_loss (hair_image_loss)" if args.impl == "mine" else "PyTorch loss functions of the reference trainer (oracle/loss_oracle.py)",
+               "api": "per step: camera + the view's supervision maps (6 uint8 planes + float32 confidence) from pinned host memory "
+                      "(double-buffered on a copy stream), GaussianRasterizer(...)(**tensors), the trainer's image loss on the "
+                      "render, autograd backward" + (", one gh_allreduce_p2p over the gradient arena" if (use_dist and par is not None) else "") +
+                      ", loss.item() read back"}
         log(f"[bench] e2e: {ms_e2e / e2e_steps:.3f} ms/step -> {e2e_value / 1e6:.1f} M Gaussians/s (loss {last['loss']:.4g})")
 
     # ---------------------------------------------------------------- per-stage timing -> roofline
@@ -723,7 +763,7 @@ def main():
         path_gbs = path_bytes / (ms_per_step * 1e-3) / 1e9
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": N, "steps": args.steps, "warmup": args.warmup,
-            "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "ms_per_step": ms_per_step, "ms_per_step_repeats": [w / args.steps for w in windows], "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f32", "data": "synthetic",
             "config": {"workload": f"strands({args.strands}) = {P_total} Gaussians, {W}x{H}, fwd+bwd, mode={args.mode}",
                        "gaussians_per_view": P, "num_rendered": int(last["R"]), "views_cycled": args.views,

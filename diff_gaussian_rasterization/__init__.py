@@ -10,5 +10,7 @@ from gaussianhaircut_b200.rasterizer import (  # noqa: F401
     GaussianRasterizer,
     rasterize_gaussians,
     _RasterizeGaussians,
+    set_gradient_arena,
+    last_gradient_arena,
 )
 from gaussianhaircut_b200 import _C  # noqa: F401

