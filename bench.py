@@ -242,7 +242,7 @@ def main():
                         raise SystemExit(f"[bench] rank {rank}: gh_allreduce_p2p ({label}) differs from NCCL all_reduce: rel err {err}")
                     if nfl < n_arena and not torch.equal(p_obj.buffer[nfl:n_arena], x[nfl:]):
                         raise SystemExit(f"[bench] rank {rank}: gh_allreduce_p2p ({label}) touched floats outside the requested range")
-                    digest = p_obj.buffer[:n_arena].view(torch.int32).to(torch.int64).sum().reshape(1)
+                    digest = p_obj.buffer[:nfl].view(torch.int32).to(torch.int64).sum().reshape(1)      # the reduced range only
                     every = [torch.zeros_like(digest) for _ in range(N)]
                     dist.all_gather(every, digest)
                     if any(int(t) != int(every[0]) for t in every):
@@ -710,13 +710,18 @@ def main():
             opt8 = FusedAdam([{"params": [getattr(pc, n)], "lr": lr, "name": n} for n, lr in zip(pnames, lrs8)], eps=1e-15)
             pipe_ns = types.SimpleNamespace(debug=False)
 
+            ws_l = torch.empty(ghl.workspace_elems(W, H), dtype=torch.float64, device=device)
+            nan_flag = torch.zeros(1, dtype=torch.int32, device=device)
+            renderer.set_nan_flag(nan_flag)      # the NaN guard rides on the projection backward
+
             def full_iter(i):
                 renders, radii, viewspace = renderer.render_raw(cam_ns, pc, pipe_ns, bg_t)
-                loss, _parts = ghl.hair_image_loss(renders, gt_image, gt_mask, gt_angle, gt_conf, *lambdas)
-                loss.backward()
-                opt8.step()
+                # loss value + dL/d(render) in one native call; the gradient goes straight into the render's backward
+                losses8, dLr = ghl.image_loss_forward_backward(renders.detach(), gt_image, gt_mask, gt_angle, gt_conf, *lambdas, workspace=ws_l)
+                renders.backward(dLr)
+                opt8.step(nan_flag_in=nan_flag)
                 opt8.zero_grad(set_to_none=True)
-                last["loss"] = loss
+                last["loss"] = losses8[0]
             how = "renderer.render_raw (gh_project_forward/backward + rasterizer) -> gh_image_loss -> FusedAdam (8 tensors)"
         elif ref_python.available():
             gr = ref_python.load_renderer("ref")
@@ -750,6 +755,8 @@ def main():
             for i in range(3):
                 full_iter(i)
             ms_full = timed(max(5, args.steps // 2), full_iter) / max(5, args.steps // 2)
+            if args.impl == "mine":
+                renderer.set_nan_flag(None)
             train_full = {"ms_per_step": ms_full, "value": P_total / (ms_full * 1e-3), "unit": UNIT, "how": how,
                           "parameters": list(pnames), "loss": float(last["loss"].detach())}
             log(f"[bench] train_gaussians.py iteration from raw parameters: {ms_full:.3f} ms/step (loss {train_full['loss']:.5f})")

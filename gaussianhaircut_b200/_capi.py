@@ -90,7 +90,7 @@ SIGNATURES = {
         _p, _p, _p, _p,                      # dL_dmeans2D dL_dconic dL_dcolors dL_dopacity
         _p, _p, _p, _p, _p, _p,              # d_xyz d_scaling d_rotation d_dirs d_features_dc d_features_rest
         _p, _p, _p, _p, _p,                  # d_opacity d_label d_orient_conf d_means2D d_camera
-        _p, _p]),                            # workspace stream
+        _p, _p, _p]),                        # nan_flag workspace stream
     "gh_debug_export": (_i, [_i, _i, _i, _ll, _p, _p, _p, _p, _p, _p, _p, _p, _p, _p, _p, _p]),
 }
 

@@ -77,10 +77,11 @@ struct GhImgWS {
     uint32_t* tile_count;    // [T]   instances per tile
     uint32_t* tile_cursor;   // [T]   emit cursors
     uint2* ranges;           // [T]   (start, end) into the sorted instance list; (0,0) if empty
+    uint32_t* tile_perm;     // [T]   launch order of the blend kernels: tiles by decreasing list length
     float* final_T;          // [W*H]
     uint32_t* n_contrib;     // [W*H] 1-based list position of the last blended instance
     static __host__ __device__ size_t bytes(size_t npix, size_t T) {
-        return 256 + 2 * gh_align_up(T * 4, 256) + gh_align_up(T * 8, 256) +
+        return 256 + 3 * gh_align_up(T * 4, 256) + gh_align_up(T * 8, 256) +
                2 * gh_align_up(npix * 4, 256) + 256;
     }
     static __host__ __device__ GhImgWS carve(char* base, size_t npix, size_t T) {
@@ -90,6 +91,7 @@ struct GhImgWS {
         w.tile_count = (uint32_t*)(base + off); off += gh_align_up(T * 4, 256);
         w.tile_cursor = (uint32_t*)(base + off); off += gh_align_up(T * 4, 256);
         w.ranges = (uint2*)(base + off); off += gh_align_up(T * 8, 256);
+        w.tile_perm = (uint32_t*)(base + off); off += gh_align_up(T * 4, 256);
         w.final_T = (float*)(base + off); off += gh_align_up(npix * 4, 256);
         w.n_contrib = (uint32_t*)(base + off);
         return w;

@@ -105,7 +105,8 @@ gh_project_backward_kernel(GhProjArgs A, const unsigned char* __restrict__ mask,
                            float* __restrict__ d_opacity, float* __restrict__ d_label, float* __restrict__ d_conf,
                            float* __restrict__ d_mean2D_out,
                            float* __restrict__ cam_partial, unsigned int* __restrict__ cam_ticket,
-                           float* __restrict__ d_cam)     // 16 V + 16 Pm + 3 campos + 2 tan, or NULL
+                           float* __restrict__ d_cam,     // 16 V + 16 Pm + 3 campos + 2 tan, or NULL
+                           unsigned int* __restrict__ nan_flag)   // set to 1 if any parameter gradient is NaN, or NULL
 {
     __shared__ __align__(16) float s_rest[GH_PJ_THREADS * GH_PJ_REST];
     __shared__ float s_cam[GH_PJ_THREADS / 32][GH_PJ_NCAM];
@@ -161,6 +162,18 @@ gh_project_backward_kernel(GhProjArgs A, const unsigned char* __restrict__ mask,
         if (d_opacity) d_opacity[i] = go.opacity;
         if (d_label) d_label[i] = go.label;
         if (d_conf) d_conf[i] = go.conf;
+    }
+    if (nan_flag != nullptr) {
+        // the optimizer's NaN guard (train_gaussians.py:174-181) rides on the kernel that produces the gradients
+        float acc = go.opacity + go.label + go.conf;
+#pragma unroll
+        for (int k = 0; k < 3; k++) acc += go.xyz[k] + go.scaling[k] + go.dirs[k] + go.f_dc[k];
+#pragma unroll
+        for (int k = 0; k < 4; k++) acc += go.rotation[k];
+#pragma unroll
+        for (int k = 0; k < GH_PJ_REST; k++) acc += go.rest[k];
+        // a sum is NaN iff a term is NaN or +inf and -inf meet: both must stop the step
+        if (__any_sync(0xffffffffu, acc != acc) && (threadIdx.x & 31) == 0) atomicOr(nan_flag, 1u);
     }
     // f_rest gradients leave through shared memory (coalesced 128-bit stores)
     __syncthreads();                                   // every thread is done reading its coefficients
@@ -301,7 +314,7 @@ extern "C" int gh_project_backward(
     const float* dL_dmeans2D, const float* dL_dconic, const float* dL_dcolors, const float* dL_dopacity,
     float* d_xyz, float* d_scaling, float* d_rotation, float* d_dirs, float* d_features_dc, float* d_features_rest,
     float* d_opacity, float* d_label, float* d_orient_conf, float* d_means2D, float* d_camera,
-    void* workspace, gh_stream_t stream_)
+    unsigned int* nan_flag, void* workspace, gh_stream_t stream_)
 {
     cudaStream_t stream = (cudaStream_t)stream_;
     gh_clear_error();
@@ -329,7 +342,7 @@ extern "C" int gh_project_backward(
     gh_project_backward_kernel<<<(P + GH_PJ_THREADS - 1) / GH_PJ_THREADS, GH_PJ_THREADS, 0, stream>>>(
         A, visible, acc16, dL_dmeans2D, dL_dconic, dL_dcolors, dL_dopacity,
         d_xyz, d_scaling, d_rotation, d_dirs, d_features_dc, d_features_rest, d_opacity, d_label, d_orient_conf,
-        d_means2D, partial, ticket, d_camera);
+        d_means2D, partial, ticket, d_camera, nan_flag);
     gh_count_launches(1);
     const cudaError_t e = cudaGetLastError();
     return e == cudaSuccess ? GH_OK : gh_set_error(GH_E_CUDA, cudaGetErrorString(e));

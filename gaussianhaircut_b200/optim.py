@@ -135,6 +135,8 @@ class FusedAdam:
                 C.c_void_p(own_nan.data_ptr()) if own_nan is not None else None,
                 C.c_void_p(skip.data_ptr()) if skip is not None else None,
                 C.c_void_p(torch.cuda.current_stream(dev).cuda_stream)))
+        if nan_flag_in is not None:
+            nan_flag_in.zero_()       # consumed: ready for the next iteration's backward (stream-ordered after the update)
         self._keep = (ps, gs, skip)   # keep the tensors alive until the kernels have run
 
     # ------------------------------------------------------------------------------------------ (de)serialisation

@@ -150,11 +150,12 @@ def _camera_workspace(P: int, dev: torch.device) -> torch.Tensor:
 
 def project_backward(pi: ProjectionInputs, visible: torch.Tensor, geom_buffer: Optional[torch.Tensor] = None,
                      dL_dmeans2D=None, dL_dconic4=None, dL_dcolors=None, dL_dopacity=None,
-                     camera_grads: bool = True, want_means2D_grad: bool = False):
+                     camera_grads: bool = True, want_means2D_grad: bool = False, nan_flag: Optional[torch.Tensor] = None):
     """Incoming gradients: either the rasterizer's geometry workspace after `gh_backward` (its accumulation records are
     read directly) or the four API-shaped tensors (dL_dmeans2D (P,3), dL_dconic (P,2,2) native layout, dL_dcolors
     (P,10), dL_dopacity (P,1)).  -> dict of parameter gradients (+ 'viewmatrix' (4,4), 'projmatrix' (4,4), 'campos' (3),
-    'tanfov' (2) when `camera_grads`, + 'means2D' (P,3) = the incoming NDC gradient when `want_means2D_grad`)."""
+    'tanfov' (2) when `camera_grads`, + 'means2D' (P,3) = the incoming NDC gradient when `want_means2D_grad`).
+    `nan_flag` (device int32[1], zeroed by the caller): OR-ed with 1 when a parameter gradient is NaN."""
     lib = _capi.load()
     dev, P = pi.device, pi.P
     f = dict(dtype=torch.float32, device=dev)
@@ -175,7 +176,8 @@ def project_backward(pi: ProjectionInputs, visible: torch.Tensor, geom_buffer: O
                 _ptr(_f32(dL_dmeans2D, "dL_dmeans2D", dev)), _ptr(conic4), _ptr(_f32(dL_dcolors, "dL_dcolors", dev, align=8)),
                 _ptr(_f32(dL_dopacity, "dL_dopacity", dev)),
                 _ptr(g["xyz"]), _ptr(g["scaling"]), _ptr(g["rotation"]), _ptr(g["dirs"]), _ptr(g["f_dc"]), _ptr(g["f_rest"]),
-                _ptr(g["opacity"]), _ptr(g["label"]), _ptr(g["conf"]), _ptr(g["means2D"]), _ptr(cam), _ptr(ws), _stream(dev)))
+                _ptr(g["opacity"]), _ptr(g["label"]), _ptr(g["conf"]), _ptr(g["means2D"]), _ptr(cam), _ptr(nan_flag), _ptr(ws),
+                _stream(dev)))
     if camera_grads:
         g["viewmatrix"], g["projmatrix"] = cam[0:16].view(4, 4), cam[16:32].view(4, 4)
         g["campos"], g["tanfov"] = cam[32:35], cam[35:37]

@@ -25,14 +25,43 @@ import torch.nn.functional as F
 
 from . import _C, projection
 
-__all__ = ["render", "render_hair", "render_raw"]
+__all__ = ["render", "render_hair", "render_raw", "set_nan_flag"]
 
 _EMPTY = torch.Tensor([])
 
+# The optimizer's NaN guard (src/train_gaussians.py:174-181) without a pass over the gradients: when a flag tensor is
+# installed, the projection backward ORs 1 into it if any parameter gradient is NaN; hand the same tensor to
+# FusedAdam.step(nan_flag_in=...).  The caller zeroes it once per iteration (FusedAdam does, after reading it).
+_NAN_FLAG = {"t": None}
+
+
+def set_nan_flag(flag):
+    """Install (or remove with None) the device int32[1] tensor that receives the NaN verdict of the next backward."""
+    _NAN_FLAG["t"] = flag
+
+
+_TAN_CACHE: Dict[int, tuple] = {}
+
 
 def _tan_half(fov) -> float:
+    """tan(fov / 2) as a host float.  The reference reads it back from the device on every call (`.item()`,
+    __init__.py:43-44); here the value is cached per FoV tensor (identity + in-place version), so a camera whose
+    field of view does not change costs one device read in total."""
     if isinstance(fov, torch.Tensor):
-        return float(torch.tan(fov.detach() * 0.5).item())          # the reference syncs here as well (__init__.py:43-44)
+        key = id(fov)
+        hit = _TAN_CACHE.get(key)
+        if hit is not None and hit[0]() is fov and hit[1] == fov._version and not fov.requires_grad:
+            return hit[2]
+        val = float(torch.tan(fov.detach() * 0.5).item())
+        if not fov.requires_grad:
+            import weakref
+            if len(_TAN_CACHE) > 4096:
+                _TAN_CACHE.clear()
+            try:
+                _TAN_CACHE[key] = (weakref.ref(fov), fov._version, val)
+            except TypeError:
+                pass
+        return val
     return math.tan(float(fov) * 0.5)
 
 
@@ -86,7 +115,8 @@ class _FusedRender(torch.autograd.Function):
         if n_head == 0:
             _C.rasterize_gaussians_backward_records(st["bg"], means3D, radii, colors, conic, pi.V, pi.Pm, st["tanx"], st["tany"],
                                                     g_color, pi.campos, geom, ctx.R, binning, img, st["debug"])
-            g = projection.project_backward(pi, visible, geom_buffer=geom, camera_grads=cam_grads, want_means2D_grad=True)
+            g = projection.project_backward(pi, visible, geom_buffer=geom, camera_grads=cam_grads, want_means2D_grad=True,
+                                            nan_flag=_NAN_FLAG["t"])
             g_view = g["means2D"]
         else:
             g9 = _C.rasterize_gaussians_backward(st["bg"], means3D, radii, colors, _EMPTY, _EMPTY, st["mod"], _EMPTY, conic,
@@ -94,7 +124,8 @@ class _FusedRender(torch.autograd.Function):
                                                  pi.campos, geom, ctx.R, binning, img, st["debug"])
             g_m2, g_col, g_op, _g3, _gc3, g_conic = g9[0], g9[1], g9[2], g9[3], g9[4], g9[5]
             g = projection.project_backward(pi, visible[n_head:], dL_dmeans2D=g_m2[n_head:], dL_dconic4=g_conic[n_head:],
-                                            dL_dcolors=g_col[n_head:], dL_dopacity=g_op[n_head:], camera_grads=cam_grads)
+                                            dL_dcolors=g_col[n_head:], dL_dopacity=g_op[n_head:], camera_grads=cam_grads,
+                                            nan_flag=_NAN_FLAG["t"])
             g_view = g_m2                  # `viewspace_points.grad` covers head rows too (retain_grad on the concatenation, :134-137)
             if cam_grads:
                 # the head block is frozen, but its conic / depth / view direction still depend on the camera; only its

@@ -264,7 +264,9 @@ int gh_allreduce_p2p(const unsigned long long* peer_bufs, const unsigned long lo
  *   any of d_dirs, d_opacity, d_label, d_orient_conf, d_means2D may be NULL.  d_camera (device float[37], or NULL):
  *   dL/dviewmatrix (16), dL/dprojmatrix (16), dL/dcampos (3), dL/dtan_fovx, dL/dtan_fovy -- summed per CTA and then
  *   in a fixed order by the last CTA (deterministic); needs `workspace` (gh_project_workspace_size bytes,
- *   16-byte aligned).
+ *   16-byte aligned).  nan_flag (device uint, or NULL): OR-ed with 1 when any per-Gaussian gradient is NaN -- the
+ *   optimizer's NaN guard without a second pass over the gradients (pass it to gh_adam_step as skip_flag; the caller
+ *   zeroes it).
  */
 int gh_project_workspace_size(int P, size_t* bytes);
 int gh_project_forward(
@@ -288,7 +290,7 @@ int gh_project_backward(
     const float* dL_dmeans2D, const float* dL_dconic, const float* dL_dcolors, const float* dL_dopacity,
     float* d_xyz, float* d_scaling, float* d_rotation, float* d_dirs, float* d_features_dc, float* d_features_rest,
     float* d_opacity, float* d_label, float* d_orient_conf, float* d_means2D, float* d_camera,
-    void* workspace, gh_stream_t stream);
+    unsigned int* nan_flag, void* workspace, gh_stream_t stream);
 
 #ifdef __cplusplus
 }

@@ -187,6 +187,46 @@ def test_fused_render_hair_matches_the_reference_pipeline(cuda_device):
     assert rel_err(pa["viewspace_points"].grad, pb["viewspace_points"].grad) <= 2 * REL_TOL
 
 
+def test_nan_guard_rides_on_the_projection_backward(cuda_device):
+    """renderer.set_nan_flag: a NaN anywhere in the parameter gradients raises the device flag during the backward;
+    FusedAdam(nan_flag_in=...) then skips the step like the reference trainer (train_gaussians.py:174-181), without a
+    pass over the gradients and without a host sync."""
+    import types
+    from gaussianhaircut_b200 import renderer
+    from gaussianhaircut_b200.optim import FusedAdam
+    synth = _util.synth
+    scene = synth.make_strand_scene(40, seed=6)
+    raw = synth.raw_params_from_scene(scene, "gaussian_model")
+    cam = ref_python.make_camera(synth.make_camera(3, 160, 96), cuda_device)
+    bg = torch.tensor(synth.BG_DEFAULT, device=cuda_device)
+    names = ("_xyz", "_features_dc", "_features_rest", "_opacity", "_label", "_scaling", "_rotation", "_orient_conf")
+    keys = ("xyz", "f_dc", "f_rest", "opacity", "label", "scaling", "rotation", "conf")
+    pc = types.SimpleNamespace(active_sh_degree=3, max_sh_degree=3)
+    for n, k in zip(names, keys):
+        setattr(pc, n, torch.nn.Parameter(raw[k].to(cuda_device).contiguous()))
+    opt = FusedAdam([{"params": [getattr(pc, n)], "lr": 1e-3, "name": n} for n in names], eps=1e-15)
+    flag = torch.zeros(1, dtype=torch.int32, device=cuda_device)
+    renderer.set_nan_flag(flag)
+    try:
+        dL = torch.rand(10, 96, 160, device=cuda_device)
+        for poisoned in (False, True, False):
+            before = pc._xyz.detach().clone()
+            renders, _r, _v = renderer.render_raw(cam, pc, types.SimpleNamespace(debug=False), bg)
+            g = dL.clone()
+            if poisoned:
+                g[0, 40:60, 60:100] = float("nan")
+            renders.backward(g)
+            assert bool(flag.item() != 0) == poisoned
+            opt.step(nan_flag_in=flag)
+            opt.zero_grad()
+            torch.cuda.synchronize()
+            assert int(flag.item()) == 0                       # consumed
+            assert torch.equal(before, pc._xyz.detach()) == poisoned, "a poisoned step must leave the parameters untouched"
+        assert opt.step_count == 2
+    finally:
+        renderer.set_nan_flag(None)
+
+
 def test_projection_api_errors(cuda_device):
     from gaussianhaircut_b200 import projection
     synth = _util.synth

@@ -47,9 +47,10 @@ def test_no_torch_types_in_abi():
 def test_workspace_size_queries(lib):
     g, i, b = C.c_size_t(), C.c_size_t(), C.c_size_t()
     assert lib.gh_forward_workspace_sizes(500000, 1920, 1080, C.byref(g), C.byref(i)) == 0
-    # 100 B per Gaussian (32 B 2-D state + 4 B depth + 64 B backward accumulation record); per pixel 8 B + per tile 16 B
+    # 100 B per Gaussian (32 B 2-D state + 4 B depth + 64 B backward accumulation record); per pixel 8 B + per tile 20 B
+    # (histogram, cursor, ranges, launch-order permutation)
     assert 100 * 500000 <= g.value <= 100 * 500000 + 4096
-    assert 8 * 1920 * 1080 + 16 * 8160 <= i.value <= 8 * 1920 * 1080 + 16 * 8160 + 4096
+    assert 8 * 1920 * 1080 + 20 * 8160 <= i.value <= 8 * 1920 * 1080 + 20 * 8160 + 4096
     assert lib.gh_binning_workspace_size(1217212, C.byref(b)) == 0
     R = 1217212
     assert 16 * R <= b.value <= 16 * R + 8 * (R // 768 + R // 2048 + 2) + 1024   # records + scratch + segment list of the long-list sort

@@ -55,6 +55,9 @@ def main():
     fshape = {(k, sh): 0 for k in (256, 512) for sh in SHAPES}
     fpairs = 0
     inst_total = inst_contrib = inst_hit = inst_reached = 0
+    ALT = ((4, 2), (2, 2), (2, 4), (8, 2), (4, 4))
+    alt = {(bw, bh_, k): [0, 0] for (bw, bh_) in ALT for k in (256, 512)}
+    alt_pix = {sh: 0 for sh in ALT}
     PSHAPES = ((2, 16), (4, 8))            # forward with a vertical pixel pair per lane: warp = row pairs x columns
     fpair_steps = {(k, sh): 0 for k in (256, 512) for sh in PSHAPES}
     fpair_entries = 0
@@ -96,6 +99,25 @@ def main():
         order = torch.argsort(c.sum(0))
         tot_sorted += int(c[:, order].view(nch, 4, 8).max(2).values.sum())
         tot_ideal += int(((c.sum(1) + 7) // 8).sum())
+        # alternative block shapes (bw x bh pixels, lanes own vertical pixel pairs -> lanes per block = bw * bh / 2):
+        # (block, G) pairs, pixels evaluated, warp steps of the lock-step walk with length-ranked block->warp assignment
+        for (bw, bh_) in ALT:
+            nbx, nby = 16 // bw, 16 // bh_
+            bid = ((ys // bh_) * nbx + (xs // bw)).reshape(-1)
+            nblk = nbx * nby
+            lanes_per_block = bw * bh_ // 2
+            per_warp = 32 // lanes_per_block
+            hb = torch.stack([hit[:, bid == k].any(1) for k in range(nblk)], 1)
+            gl2 = torch.stack([nc.reshape(-1)[bid == k].max() for k in range(nblk)])
+            hb &= pos < gl2[None]
+            for k in (256, 512):
+                n = (L + k - 1) // k
+                cb = torch.nn.functional.pad(hb.int(), (0, 0, 0, n * k - L)).view(n, k, nblk).sum(1)      # [chunk, block]
+                order2 = torch.argsort(cb[-1])             # ranking from the last window, like the kernel
+                steps = int(cb[:, order2].view(n, nblk // per_warp, per_warp).max(2).values.sum())
+                a = alt[(bw, bh_, k)]
+                a[0] += int(cb.sum()); a[1] += steps
+            alt_pix[(bw, bh_)] += int(hb.sum()) * bw * bh_
         fh = hit & (pos < nc.reshape(-1).max())                             # forward: tile-wide early exit only
         fpairs += int(fh.sum())
         for k in CH:
@@ -128,6 +150,13 @@ def main():
     for k in CH:
         print(f"backward lock-step window {k:5d}: steps {bsteps[k][0]} (eff {tot_pairs / 8 / bsteps[k][0]:.3f})   "
               f"sorted {bsteps[k][1]} (eff {tot_pairs / 8 / bsteps[k][1]:.3f})")
+    for (bw, bh_) in ALT:
+        for k in (256, 512):
+            pairs, steps = alt[(bw, bh_, k)]
+            lpb = bw * bh_ // 2
+            print(f"backward blocks {bw}x{bh_} ({lpb} lanes/block, {32 // lpb} blocks/warp) window {k}: (block,G) pairs {pairs}, pixel eff "
+                  f"{tot_pix / max(1, alt_pix[(bw, bh_)]):.3f}, warp steps {steps} (lane eff {pairs * lpb / 32 / max(1, steps):.3f}), "
+                  f"pixel-pairs evaluated per contributing pixel {steps * 16 / max(1, tot_pix) * 2:.2f}")
     for k in CH:
         print(f"forward  lock-step window {k:5d}: warp steps {fsteps[k]} (lane eff {fpairs / 32 / fsteps[k]:.3f})")
     print(f"forward pixel entries {fpairs}; pixel-PAIR entries {fpair_entries} ({fpair_entries / fpairs:.3f} of single)")
