@@ -1,0 +1,166 @@
+"""Adaptive density control ("next" row 3 of SURVEY.md 8f): `densify_and_prune` and `reset_opacity` with the
+reference's semantics (src/scene/gaussian_model.py:723-737, :516-519; called from src/train_gaussians.py:160-171),
+operating IN PLACE on a GaussianModel-shaped object (its `_xyz ... _orient_conf` parameters, `optimizer`,
+`xyz_gradient_accum`, `denom`, `max_radii2D`, `percent_dense`) -- a trainer replaces
+
+    gaussians.densify_and_prune(max_grad, min_opacity, extent, max_screen_size)
+by  densify.densify_and_prune(gaussians, max_grad, min_opacity, extent, max_screen_size)
+
+The reference runs three rounds (clone, split, prune) that each rebuild every parameter and both Adam moments with
+boolean-mask gathers and torch.cat and then calls torch.cuda.empty_cache(); here one classification kernel decides the
+fate of every Gaussian, a prefix sum assigns final row positions, and one compaction kernel writes every parameter and
+both moments exactly once, in the reference's resulting order (csrc/gh_densify.cu).  The random offsets of split
+children are drawn with the SAME torch call the reference makes (torch.normal on the same shapes), so a run seeded like
+the reference produces the same children -- and ranks of a data-parallel job that seed identically stay identical.
+Works with torch.optim.Adam and with gaussianhaircut_b200.optim.FusedAdam (same `param_groups` / `state` surface).
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Dict, List, Optional
+
+import torch
+from torch import nn
+
+from . import _capi
+
+# optimizer group name -> model attribute (src/scene/gaussian_model.py:431-442, :621-628)
+GROUPS = {"xyz": "_xyz", "f_dc": "_features_dc", "f_rest": "_features_rest", "opacity": "_opacity", "label": "_label",
+          "scaling": "_scaling", "rotation": "_rotation", "orient_conf": "_orient_conf"}
+
+
+def _ptr(t: Optional[torch.Tensor]):
+    return None if t is None else C.c_void_p(t.data_ptr())
+
+
+def _stream(dev):
+    return C.c_void_p(torch.cuda.current_stream(dev).cuda_stream)
+
+
+def classify(gaussians, max_grad: float, min_opacity: float, extent: float, max_screen_size) -> torch.Tensor:
+    """(P,4) int32 flags: [original survives, its clone survives, its two children survive, it is split]."""
+    lib = _capi.load()
+    xyz = gaussians._xyz
+    dev, P = xyz.device, int(xyz.shape[0])
+    if not xyz.is_cuda:
+        raise RuntimeError("gaussianhaircut_b200.densify: tensors must live on a CUDA device (no CPU path)")
+    flags = torch.empty((P, 4), dtype=torch.int32, device=dev)
+    if P == 0:
+        return flags
+    acc = gaussians.xyz_gradient_accum.detach().reshape(-1).contiguous().float()
+    den = gaussians.denom.detach().reshape(-1).contiguous().float()
+    if acc.numel() != P or den.numel() != P:
+        raise RuntimeError("densify: xyz_gradient_accum / denom must have one entry per Gaussian")
+    ws_limit = float(0.1 * extent) if max_screen_size else 0.0
+    with torch.cuda.device(dev):
+        _capi.check(lib.gh_densify_classify(
+            P, _ptr(acc), _ptr(den), _ptr(gaussians._scaling.detach().contiguous()), _ptr(gaussians._opacity.detach().contiguous()),
+            float(max_grad), float(gaussians.percent_dense * extent), float(min_opacity), ws_limit, _ptr(flags), _stream(dev)))
+    return flags
+
+
+def densify_and_prune(gaussians, max_grad: float, min_opacity: float, extent: float, max_screen_size,
+                      empty_cache: bool = False) -> Dict[str, int]:
+    """In-place equivalent of GaussianModel.densify_and_prune.  Returns the counts
+    {'kept', 'cloned', 'split', 'children', 'total'} (host ints; the one device->host read of the call)."""
+    lib = _capi.load()
+    opt = gaussians.optimizer
+    dev = gaussians._xyz.device
+    P = int(gaussians._xyz.shape[0])
+    flags = classify(gaussians, max_grad, min_opacity, extent, max_screen_size)
+    prefix = torch.cumsum(flags, dim=0, dtype=torch.int32).contiguous()
+    totals = [int(v) for v in (prefix[-1].tolist() if P > 0 else [0, 0, 0, 0])]
+    nA, nB, nC, n_split_all = totals
+    P_new = nA + nB + 2 * nC
+
+    # the split children's offsets: exactly the reference's draw (gaussian_model.py:690-692)
+    samples = None
+    if n_split_all > 0:
+        split_mask = flags[:, 3] != 0
+        stds = torch.exp(gaussians._scaling.detach())[split_mask].repeat(2, 1)
+        means = torch.zeros((stds.size(0), 3), device=dev)
+        samples = torch.normal(mean=means, std=stds).contiguous()
+
+    # tensor table: every optimizer group (parameter + its two moments) and, when it is not optimised, orient_conf
+    by_name = {g["name"]: g for g in opt.param_groups}
+    names: List[str] = [n for n in GROUPS if n in by_name]
+    missing = [n for n in ("xyz", "f_dc", "f_rest", "opacity", "label", "scaling", "rotation") if n not in by_name]
+    if missing:
+        raise RuntimeError(f"densify: optimizer has no parameter group(s) {missing}")
+    srcs, m1s, m2s, rows, dsts, d1s, d2s = [], [], [], [], [], [], []
+    for n in names:
+        p = by_name[n]["params"][0]
+        if p.shape[0] != P or p.dtype != torch.float32 or not p.is_contiguous():
+            raise RuntimeError(f"densify: parameter group '{n}' must be a contiguous float32 tensor with {P} rows")
+        st = opt.state.get(p, None)
+        row = p.numel() // max(P, 1) if P > 0 else int(torch.tensor(p.shape[1:]).prod()) if p.dim() > 1 else 1
+        new_p = torch.empty((P_new,) + tuple(p.shape[1:]), dtype=torch.float32, device=dev)
+        srcs.append(p.detach()); rows.append(row); dsts.append(new_p)
+        if st is not None and "exp_avg" in st:
+            for k in ("exp_avg", "exp_avg_sq"):
+                if st[k].shape != p.shape or not st[k].is_contiguous():
+                    raise RuntimeError(f"densify: optimizer state '{k}' of group '{n}' does not match its parameter")
+            m1s.append(st["exp_avg"]); m2s.append(st["exp_avg_sq"])
+            d1s.append(torch.empty_like(new_p)); d2s.append(torch.empty_like(new_p))
+        else:
+            m1s.append(None); m2s.append(None); d1s.append(None); d2s.append(None)
+    n = len(names)
+    if P > 0:
+        arr = lambda ts: (C.c_void_p * n)(*[(t.data_ptr() if t is not None else None) for t in ts])   # noqa: E731
+        with torch.cuda.device(dev):
+            _capi.check(lib.gh_densify_scatter(
+                P, n, arr(srcs), arr(m1s), arr(m2s), arr(dsts), arr(d1s), arr(d2s), (C.c_int * n)(*rows),
+                names.index("xyz"), names.index("scaling"), names.index("rotation"),
+                _ptr(flags), _ptr(prefix), nA, nB, nC, _ptr(samples), n_split_all, _stream(dev)))
+
+    # install the new tensors the way the reference does (new nn.Parameter per group, state re-keyed)
+    for k, nme in enumerate(names):
+        group = by_name[nme]
+        old = group["params"][0]
+        stored = opt.state.get(old, None)
+        new_param = nn.Parameter(dsts[k].requires_grad_(True))
+        if stored is not None:
+            if d1s[k] is not None:
+                stored["exp_avg"], stored["exp_avg_sq"] = d1s[k], d2s[k]
+            del opt.state[old]
+            opt.state[new_param] = stored
+        group["params"][0] = new_param
+        setattr(gaussians, GROUPS[nme], new_param)
+    if "orient_conf" not in by_name:
+        # the reference replaces a non-optimised orient_conf by zeros of the new size (:629, :671)
+        gaussians._orient_conf = torch.zeros((P_new, 1), dtype=torch.float32, device=dev)
+    gaussians.xyz_gradient_accum = torch.zeros((P_new, 1), device=dev)
+    gaussians.denom = torch.zeros((P_new, 1), device=dev)
+    gaussians.max_radii2D = torch.zeros((P_new,), device=dev)
+    if empty_cache:
+        torch.cuda.empty_cache()          # the reference always does (:737); it stalls the allocator, so it is opt-in here
+    return {"kept": nA, "cloned": nB, "split": n_split_all, "children": 2 * nC, "total": P_new}
+
+
+def reset_opacity(gaussians) -> None:
+    """GaussianModel.reset_opacity (src/scene/gaussian_model.py:516-519): opacity <- min(opacity, 0.01) in logit space,
+    optimizer moments of the group zeroed (replace_tensor_to_optimizer :581-593)."""
+    opt = gaussians.optimizer
+    with torch.no_grad():
+        op = torch.sigmoid(gaussians._opacity)
+        new = torch.minimum(op, torch.full_like(op, 0.01))
+        new = torch.log(new / (1 - new))
+    for group in opt.param_groups:
+        if group.get("name") == "opacity":
+            old = group["params"][0]
+            stored = opt.state.get(old, None)
+            new_param = nn.Parameter(new.contiguous().requires_grad_(True))
+            if stored is not None:
+                stored["exp_avg"] = torch.zeros_like(new_param)
+                stored["exp_avg_sq"] = torch.zeros_like(new_param)
+                del opt.state[old]
+                opt.state[new_param] = stored
+            group["params"][0] = new_param
+            gaussians._opacity = new_param
+
+
+def add_densification_stats(gaussians, viewspace_point_tensor, update_filter) -> None:
+    """GaussianModel.add_densification_stats (:739-741) -- unchanged arithmetic, here for completeness of the loop."""
+    g = viewspace_point_tensor.grad
+    gaussians.xyz_gradient_accum[update_filter] += torch.norm(g[update_filter, :2], dim=-1, keepdim=True)
+    gaussians.denom[update_filter] += 1

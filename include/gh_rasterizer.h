@@ -292,6 +292,34 @@ int gh_project_backward(
     float* d_opacity, float* d_label, float* d_orient_conf, float* d_means2D, float* d_camera,
     unsigned int* nan_flag, void* workspace, gh_stream_t stream);
 
+/*
+ * "Next" row: adaptive density control -- the outcome of the reference's densify_and_prune
+ * (src/scene/gaussian_model.py:723-737 = densify_and_clone :708-721 + densify_and_split :682-706 + prune_points
+ * :613-630, each re-allocating every parameter and both Adam moments with mask gathers / torch.cat :595-654) in one
+ * classification pass and one compaction pass.
+ * gh_densify_classify: flags (P,4) int32, 16-byte aligned = [original survives (not split, not pruned), its clone
+ *   survives, its two children survive, it is split (before the prune)].  grad_threshold / dense_extent
+ *   (= percent_dense * scene extent) / min_opacity as in the reference; ws_limit = 0.1 * extent when the caller passes
+ *   a max_screen_size, else 0 (test disabled).  The screen-size test itself never fires in the reference
+ *   (max_radii2D is zeroed by densification_postfix before it is read, :674) and is therefore not an input.
+ * gh_densify_scatter: src / exp_avg / exp_avg_sq / dst / dst_* are HOST arrays of n_tensors (<= 8) device pointers
+ *   (row-major (P, row_floats[k]); exp_avg[k] NULL = tensor without optimizer state).  inclusive_prefix = inclusive
+ *   prefix sums of flags over the Gaussians (P,4), n_keep / n_clone / n_split_kept = the totals of columns 0..2.
+ *   samples (2 * n_split_all, 3): N(0, scale) draws, first-children block then second-children block
+ *   (torch.normal(mean=0, std=get_scaling[mask].repeat(2, 1)), :690-692).  Destination rows follow the reference's
+ *   order [surviving originals | surviving clones | first children | second children]; clones and children get zero
+ *   moments; child xyz = R(q) sample + xyz, child log-scale = log(scale / 1.6).
+ */
+int gh_densify_classify(int P, const float* grad_accum, const float* denom, const float* log_scaling,
+                        const float* opacity_logit, float grad_threshold, float dense_extent,
+                        float min_opacity, float ws_limit, int* flags, gh_stream_t stream);
+int gh_densify_scatter(int P, int n_tensors, const float* const* src, const float* const* exp_avg,
+                       const float* const* exp_avg_sq, float* const* dst, float* const* dst_exp_avg,
+                       float* const* dst_exp_avg_sq, const int* row_floats,
+                       int xyz_index, int scaling_index, int rotation_index,
+                       const int* flags, const int* inclusive_prefix, int n_keep, int n_clone, int n_split_kept,
+                       const float* samples, int n_split_all, gh_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif
