@@ -13,6 +13,7 @@ from typing import Optional, Tuple
 import torch
 
 from . import _capi
+from ._alloc import empty_rows, row_capacity
 
 NUM_CHANNELS = 10  # reference cuda_rasterizer/config.h:15
 
@@ -113,11 +114,14 @@ def rasterize_gaussians(
         background = _prep(background, "background", device)
         M = int(sh.size(1)) if sh.numel() != 0 else 0
 
-        geom_bytes, img_bytes = C.c_size_t(), C.c_size_t()
+        geom_bytes, img_bytes, geom_cap = C.c_size_t(), C.c_size_t(), C.c_size_t()
         _capi.check(lib.gh_forward_workspace_sizes(P, W, H, C.byref(geom_bytes), C.byref(img_bytes)))
-        geomBuffer = torch.empty(geom_bytes.value, **byte_opts)
+        # bucketed sizes for the per-Gaussian buffers (see _alloc.py): a model that grows a little keeps hitting the
+        # allocator's cached blocks
+        _capi.check(lib.gh_forward_workspace_sizes(row_capacity(P), W, H, C.byref(geom_cap), None))
+        geomBuffer = torch.empty(geom_cap.value, **byte_opts)[:geom_bytes.value]
         imgBuffer = torch.empty(img_bytes.value, **byte_opts)
-        radii = torch.empty((P,), dtype=torch.int32, device=device)
+        radii = empty_rows(P, (), torch.int32, device)
         out_color = torch.empty((NUM_CHANNELS, H, W), dtype=torch.float32, device=device)
         stream = _stream(device)
 

@@ -22,6 +22,7 @@ from typing import Dict, Optional
 import torch
 
 from . import _capi
+from ._alloc import empty_rows
 
 # activation / mode codes (GhProjArgs in csrc/gh_project_math.h)
 GAUSSIAN_MODEL = dict(scale_act=1, opacity_act=1, label_act=1, conf_act=1, dir_mode=0, det_eps=1e-12)   # gaussian_model.py
@@ -106,11 +107,11 @@ def _common_args(pi: ProjectionInputs):
 
 
 def alloc_outputs(P: int, dev: torch.device, want_cov3D: bool = False, means2D_out: Optional[torch.Tensor] = None):
-    f = dict(dtype=torch.float32, device=dev)
-    return {"means2D": means2D_out if means2D_out is not None else torch.empty((P, 3), **f),
-            "colors": torch.empty((P, 10), **f), "opacity": torch.empty((P, 1), **f), "conic": torch.empty((P, 3), **f),
-            "visible": torch.empty((P,), dtype=torch.uint8, device=dev),
-            "cov3D": torch.empty((P, 6), **f) if want_cov3D else None}
+    f32 = torch.float32
+    return {"means2D": means2D_out if means2D_out is not None else empty_rows(P, (3,), f32, dev),
+            "colors": empty_rows(P, (10,), f32, dev), "opacity": empty_rows(P, (1,), f32, dev), "conic": empty_rows(P, (3,), f32, dev),
+            "visible": empty_rows(P, (), torch.uint8, dev),
+            "cov3D": empty_rows(P, (6,), f32, dev) if want_cov3D else None}
 
 
 def project_forward(pi: ProjectionInputs, want_cov3D: bool = False, means2D_out: Optional[torch.Tensor] = None,
@@ -148,6 +149,46 @@ def _camera_workspace(P: int, dev: torch.device) -> torch.Tensor:
     return ws
 
 
+# parameter-gradient segments of a flat gradient arena (floats per Gaussian), in this order; every segment is padded to a
+# multiple of 4 floats so that a 4-float-granular all-reduce covers whole segments and every view stays 16-byte aligned
+GRAD_SEGMENTS = (("rotation", 4), ("xyz", 3), ("scaling", 3), ("f_dc", 3), ("f_rest", 45), ("opacity", 1), ("label", 1), ("conf", 1),
+                 ("dirs", 3))
+
+
+def grad_arena_floats(P: int, with_dirs: bool = False) -> int:
+    """float32 elements of the model-gradient arena for P Gaussians (61 per Gaussian + padding; +3 with `dirs`)."""
+    return sum((P * n + 3) // 4 * 4 for k, n in GRAD_SEGMENTS if with_dirs or k != "dirs")
+
+
+def carve_grad_arena(storage: torch.Tensor, P: int, with_dirs: bool = False) -> Dict[str, torch.Tensor]:
+    need = grad_arena_floats(P, with_dirs)
+    if storage.dtype != torch.float32 or not storage.is_contiguous() or storage.numel() < need:
+        raise RuntimeError(f"projection: gradient arena must be a contiguous float32 tensor of at least {need} elements")
+    flat = storage.view(-1)
+    out, off = {}, 0
+    shapes = {"f_dc": (P, 1, 3), "f_rest": (P, 15, 3)}
+    for k, n in GRAD_SEGMENTS:
+        if k == "dirs" and not with_dirs:
+            continue
+        out[k] = flat[off:off + P * n].view(shapes.get(k, (P, n)))
+        off += (P * n + 3) // 4 * 4
+    return out
+
+
+# process-wide, like rasterizer.set_gradient_arena (autograd's backward thread must see it)
+_GRAD_ARENA = {"storage": None, "last": None}
+
+
+def set_gradient_arena(storage):
+    """Install (or remove with None) a caller-owned flat float32 buffer -- e.g. dist.PeerAllReduce(...).buffer -- into
+    which the next projection backward writes every parameter gradient (`carve_grad_arena` layout), so that a
+    data-parallel trainer reduces the whole model gradient with ONE collective over `flat[:grad_arena_floats(P)]`."""
+    prev = _GRAD_ARENA["storage"]
+    _GRAD_ARENA["storage"] = storage
+    _GRAD_ARENA["last"] = None
+    return prev
+
+
 def project_backward(pi: ProjectionInputs, visible: torch.Tensor, geom_buffer: Optional[torch.Tensor] = None,
                      dL_dmeans2D=None, dL_dconic4=None, dL_dcolors=None, dL_dopacity=None,
                      camera_grads: bool = True, want_means2D_grad: bool = False, nan_flag: Optional[torch.Tensor] = None):
@@ -159,13 +200,24 @@ def project_backward(pi: ProjectionInputs, visible: torch.Tensor, geom_buffer: O
     lib = _capi.load()
     dev, P = pi.device, pi.P
     f = dict(dtype=torch.float32, device=dev)
-    g = {"xyz": torch.empty((P, 3), **f), "scaling": torch.empty((P, 3), **f), "rotation": torch.empty((P, 4), **f),
-         "dirs": torch.empty((P, 3), **f) if pi.dirs is not None else None,
-         "f_dc": torch.empty((P, 1, 3), **f), "f_rest": torch.empty((P, 15, 3), **f),
-         "opacity": torch.empty((P, 1), **f) if pi.opacity is not None else None,
-         "label": torch.empty((P, 1), **f) if pi.label is not None else None,
-         "conf": torch.empty((P, 1), **f) if pi.conf is not None else None,
-         "means2D": torch.empty((P, 3), **f) if want_means2D_grad else None}
+    if _GRAD_ARENA["storage"] is not None:
+        a = carve_grad_arena(_GRAD_ARENA["storage"], P, with_dirs=pi.dirs is not None)
+        _GRAD_ARENA["last"] = P
+        g = {"xyz": a["xyz"], "scaling": a["scaling"], "rotation": a["rotation"], "dirs": a.get("dirs"),
+             "f_dc": a["f_dc"], "f_rest": a["f_rest"],
+             "opacity": a["opacity"] if pi.opacity is not None else None,
+             "label": a["label"] if pi.label is not None else None,
+             "conf": a["conf"] if pi.conf is not None else None}
+        del a
+    else:
+        f32 = torch.float32
+        g = {"xyz": empty_rows(P, (3,), f32, dev), "scaling": empty_rows(P, (3,), f32, dev), "rotation": empty_rows(P, (4,), f32, dev),
+             "dirs": empty_rows(P, (3,), f32, dev) if pi.dirs is not None else None,
+             "f_dc": empty_rows(P, (1, 3), f32, dev), "f_rest": empty_rows(P, (15, 3), f32, dev),
+             "opacity": empty_rows(P, (1,), f32, dev) if pi.opacity is not None else None,
+             "label": empty_rows(P, (1,), f32, dev) if pi.label is not None else None,
+             "conf": empty_rows(P, (1,), f32, dev) if pi.conf is not None else None}
+    g["means2D"] = empty_rows(P, (3,), torch.float32, dev) if want_means2D_grad else None
     cam = torch.zeros(37, **f) if camera_grads else None
     if P != 0:
         with torch.cuda.device(dev):

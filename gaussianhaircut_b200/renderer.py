@@ -24,6 +24,7 @@ import torch
 import torch.nn.functional as F
 
 from . import _C, projection
+from ._alloc import empty_rows
 
 __all__ = ["render", "render_hair", "render_raw", "set_nan_flag"]
 
@@ -171,7 +172,7 @@ def render_raw(viewpoint_camera, pc, pipe, bg_color: torch.Tensor, scaling_modif
     `losses.hair_image_loss` consumes (it contains the epilogue), so a trainer built on this repository never
     materialises the four separate maps."""
     P = int(pc._xyz.shape[0])
-    viewspace = torch.empty((P, 3), dtype=torch.float32, device=pc._xyz.device, requires_grad=True)
+    viewspace = empty_rows(P, (3,), torch.float32, pc._xyz.device).requires_grad_(True)
     st = _static(viewpoint_camera, bg_color, scaling_modifier, pc.active_sh_degree, getattr(pipe, "debug", False),
                  projection.GAUSSIAN_MODEL)
     renders, radii = _FusedRender.apply(
@@ -211,7 +212,7 @@ def render_hair(viewpoint_camera, pc, pc_hair, pipe, bg_color: torch.Tensor, sca
     n_head = int(head["xyz"].shape[0])
     P = n_head + int(pc_hair.get_xyz.shape[0])
     dev = pc_hair.get_xyz.device
-    viewspace = torch.empty((P, 3), dtype=torch.float32, device=dev, requires_grad=True)
+    viewspace = empty_rows(P, (3,), torch.float32, dev).requires_grad_(True)
     st = _static(viewpoint_camera, bg_color, scaling_modifier, pc_hair.active_sh_degree, getattr(pipe, "debug", False),
                  projection.HAIR_MODEL)
     st["head"] = head if n_head > 0 else None
