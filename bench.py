@@ -684,7 +684,7 @@ def main():
     # (oracle/ref_python.py) on its own rasterizer build -> the PyTorch losses of its trainer -> torch.optim.Adam with the
     # trainer's per-parameter NaN host syncs.
     train_full = None
-    if args.mode == "native" and not use_dist and rank == 0:
+    if args.mode == "native" and (rank == 0 or use_dist):          # at N > 1 every rank takes part (one view per rank)
         import types
         import ref_python
         gen = torch.Generator(device="cpu").manual_seed(11)
@@ -694,7 +694,7 @@ def main():
         gt_conf = torch.rand(1, H, W, generator=gen).to(device)
         lambdas = (0.8, 0.2, 0.1, 0.1)
         raw = synth.raw_params_from_scene(scene, "gaussian_model")
-        cam_d = synth.make_camera(0, W, H)
+        cam_d = synth.make_camera((rank * 8) % 64, W, H)             # rank r renders its own camera
         cam_ns = ref_python.make_camera(cam_d, device)
         bg_t = torch.tensor(synth.BG_DEFAULT, device=device)
         pnames = ("_xyz", "_features_dc", "_features_rest", "_opacity", "_label", "_scaling", "_rotation", "_orient_conf")
@@ -712,17 +712,33 @@ def main():
 
             ws_l = torch.empty(ghl.workspace_elems(W, H), dtype=torch.float64, device=device)
             nan_flag = torch.zeros(1, dtype=torch.int32, device=device)
-            renderer.set_nan_flag(nan_flag)      # the NaN guard rides on the projection backward
+            par_m = None
+            if use_dist:
+                # data parallel: the projection backward writes the model gradients (61 floats per Gaussian) into ONE
+                # symmetric-memory arena, reduced by ONE gh_allreduce_p2p; its NaN verdict and error flag gate the optimizer
+                from gaussianhaircut_b200 import projection
+                par_m = ghdist.PeerAllReduce(projection.grad_arena_floats(P_total), device,
+                                             use_multicast={"auto": None, "peer-mc": True, "peer-nomc": False, "nccl": None}[args.collective])
+                projection.set_gradient_arena(par_m.buffer)
+                order8 = ("xyz", "f_dc", "f_rest", "opacity", "label", "scaling", "rotation", "conf")
+            else:
+                renderer.set_nan_flag(nan_flag)      # single GPU: the NaN guard rides on the projection backward
 
             def full_iter(i):
                 renders, radii, viewspace = renderer.render_raw(cam_ns, pc, pipe_ns, bg_t)
                 # loss value + dL/d(render) in one native call; the gradient goes straight into the render's backward
                 losses8, dLr = ghl.image_loss_forward_backward(renders.detach(), gt_image, gt_mask, gt_angle, gt_conf, *lambdas, workspace=ws_l)
                 renders.backward(dLr)
-                opt8.step(nan_flag_in=nan_flag)
+                if par_m is not None:
+                    par_m.all_reduce(n_floats=projection.grad_arena_floats(P_total))
+                    a8 = projection.carve_grad_arena(par_m.buffer, P_total)
+                    opt8.step(grads=[a8[k] for k in order8], skip_flags=(par_m.error_flag,), nan_flag_in=par_m.nan_flag)
+                else:
+                    opt8.step(nan_flag_in=nan_flag)
                 opt8.zero_grad(set_to_none=True)
                 last["loss"] = losses8[0]
-            how = "renderer.render_raw (gh_project_forward/backward + rasterizer) -> gh_image_loss -> FusedAdam (8 tensors)"
+            how = "renderer.render_raw (gh_project_forward/backward + rasterizer) -> gh_image_loss -> " + \
+                  ("one gh_allreduce_p2p over the model-gradient arena (61 floats per Gaussian) -> " if use_dist else "") + "FusedAdam (8 tensors)"
         elif ref_python.available():
             gr = ref_python.load_renderer("ref")
             import utils.loss_utils as loss_oracle        # the reference's own loss functions (src/utils/loss_utils.py), unmodified
@@ -757,7 +773,11 @@ def main():
             ms_full = timed(max(5, args.steps // 2), full_iter) / max(5, args.steps // 2)
             if args.impl == "mine":
                 renderer.set_nan_flag(None)
-            train_full = {"ms_per_step": ms_full, "value": P_total / (ms_full * 1e-3), "unit": UNIT, "how": how,
+                if use_dist:
+                    projection.set_gradient_arena(None)
+                    if not par_m.ok():
+                        raise SystemExit("[bench] gh_allreduce_p2p reported a missing peer during the training-iteration figure")
+            train_full = {"ms_per_step": ms_full, "value": n_eff * P_total / (ms_full * 1e-3), "unit": UNIT, "how": how,
                           "parameters": list(pnames), "loss": float(last["loss"].detach())}
             log(f"[bench] train_gaussians.py iteration from raw parameters: {ms_full:.3f} ms/step (loss {train_full['loss']:.5f})")
 

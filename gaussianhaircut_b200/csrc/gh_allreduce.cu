@@ -234,9 +234,13 @@ extern "C" int gh_allreduce_p2p(const unsigned long long* peer_bufs, const unsig
     }
     float* mc = reinterpret_cast<float*>(multicast_buf);
     // every CTA waits for the entry barrier, so all of them must be resident: sms x (CTAs that fit per SM, capped)
-    const int threads = gh_env_int("GH_ALLREDUCE_THREADS", mc ? 256 : 512, 64, GH_AR_MAX_THREADS) & ~31;
-    const int mc_u = gh_env_int("GH_ALLREDUCE_UNROLL", 8, 1, 16);
-    const int want_cps = gh_env_int("GH_ALLREDUCE_CTAS_PER_SM", mc ? 4 : 1, 1, 8);
+    // defaults = the fastest point of the measured sweep at 8 GPUs / 42 MB (tools/allreduce_case.py --sweep, profiles/):
+    // the NVLS path is fastest with FEW requests in flight (128 threads, 1 CTA per SM, 2 x 16 B per thread: 121 us against
+    // 148 us at 256 threads x 4 CTAs x 8); the peer load/store path wants one full CTA per SM
+    const int threads = gh_env_int("GH_ALLREDUCE_THREADS", mc ? 128 : 512, 32, GH_AR_MAX_THREADS) & ~31;
+    const int mc_u = gh_env_int("GH_ALLREDUCE_UNROLL", 2, 1, 16);
+    const int want_cps = gh_env_int("GH_ALLREDUCE_CTAS_PER_SM", 1, 1, 8);
+    const int max_ctas = gh_env_int("GH_ALLREDUCE_MAX_CTAS", 1 << 20, 1, 1 << 20);
     const unsigned long long timeout_ns = 1000000ull * (unsigned long long)gh_env_int("GH_ALLREDUCE_TIMEOUT_MS", 30000, 1, 3600000);
     int dev = 0, sms = 0;
     if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess)
@@ -250,7 +254,8 @@ extern "C" int gh_allreduce_p2p(const unsigned long long* peer_bufs, const unsig
             cudaSuccess || occ < 1) occ = 1;                                                                       \
         const int cps = occ < want_cps ? occ : want_cps;                                                           \
         size_t want = (per_rank + threads - 1) / threads;                                                          \
-        const size_t cap = (size_t)sms * cps;                                                                      \
+        const size_t cap0 = (size_t)sms * cps;                                                                     \
+        const size_t cap = cap0 < (size_t)max_ctas ? cap0 : (size_t)max_ctas;                                      \
         const int grid = (int)(want < 1 ? 1 : (want > cap ? cap : want));                                          \
         gh_allreduce_p2p_kernel<WT, MU><<<grid, threads, 0, stream>>>(peers, mc, rank, world, offset_floats / 4,   \
                                                                       n4, epoch, local_sync, nan_out, timeout_ns); \
@@ -259,7 +264,8 @@ extern "C" int gh_allreduce_p2p(const unsigned long long* peer_bufs, const unsig
         if (mc_u >= 16) GH_AR_LAUNCH(0, 16);
         else if (mc_u >= 8) GH_AR_LAUNCH(0, 8);
         else if (mc_u >= 4) GH_AR_LAUNCH(0, 4);
-        else GH_AR_LAUNCH(0, 2);
+        else if (mc_u >= 2) GH_AR_LAUNCH(0, 2);
+        else GH_AR_LAUNCH(0, 1);
     } else if (world == 2) GH_AR_LAUNCH(2, 1);
     else if (world == 4) GH_AR_LAUNCH(4, 1);
     else if (world == 8) GH_AR_LAUNCH(8, 1);

@@ -42,12 +42,18 @@ for name, mc in (("peer ld/st", False), ("multimem", True)):
     res[name] = timed(lambda: par.all_reduce(n_floats=n))
     assert par.ok()
     if sweep:
-        grid = itertools.product((128, 256, 512), (1, 2, 4, 8), (2, 4, 8, 16) if mc else (1,))
-        for th, cps, un in grid:
-            os.environ.update(GH_ALLREDUCE_THREADS=str(th), GH_ALLREDUCE_CTAS_PER_SM=str(cps), GH_ALLREDUCE_UNROLL=str(un))
+        if mc:      # the NVLS path likes few requests in flight: sweep downwards too (grid smaller than the SM count)
+            grid = itertools.product((64, 128, 256, 512), (1, 2), (1, 2, 4, 8), (37, 74, 148, 1 << 20))
+        else:
+            grid = itertools.product((128, 256, 512), (1, 2, 4), (1,), (1 << 20,))
+        for th, cps, un, mx in grid:
+            if mx != 1 << 20 and cps > 1:
+                continue
+            os.environ.update(GH_ALLREDUCE_THREADS=str(th), GH_ALLREDUCE_CTAS_PER_SM=str(cps), GH_ALLREDUCE_UNROLL=str(un),
+                              GH_ALLREDUCE_MAX_CTAS=str(mx))
             t = timed(lambda: par.all_reduce(n_floats=n))
-            table.append({"path": name, "threads": th, "ctas_per_sm": cps, "unroll": un, "us": t})
-        for k in ("GH_ALLREDUCE_THREADS", "GH_ALLREDUCE_CTAS_PER_SM", "GH_ALLREDUCE_UNROLL"):
+            table.append({"path": name, "threads": th, "ctas_per_sm": cps, "unroll": un, "max_ctas": mx, "us": t})
+        for k in ("GH_ALLREDUCE_THREADS", "GH_ALLREDUCE_CTAS_PER_SM", "GH_ALLREDUCE_UNROLL", "GH_ALLREDUCE_MAX_CTAS"):
             os.environ.pop(k, None)
     assert par.ok()
 if rank == 0:
@@ -57,6 +63,6 @@ if rank == 0:
         for path in ("peer ld/st", "multimem"):
             rows = sorted((r for r in table if r["path"] == path), key=lambda r: r["us"])
             for r in rows[:6]:
-                print(f"  {path}: threads {r['threads']} ctas/SM {r['ctas_per_sm']} unroll {r['unroll']}: {r['us']:.1f} us")
+                print(f"  {path}: threads {r['threads']} ctas/SM {r['ctas_per_sm']} unroll {r['unroll']} max CTAs {r['max_ctas']}: {r['us']:.1f} us")
         print(json.dumps({"world": world, "mb": mb, "defaults": res, "sweep": table}))
 dist.destroy_process_group()
