@@ -1,9 +1,11 @@
-"""gh_image_loss at 1920x1080 on synthetic maps (for ncu / timing): python tools/loss_case.py [reps]"""
+"""gh_image_loss at 1920x1080 on synthetic maps (for ncu / timing): python tools/loss_case.py [reps] [variant .so]"""
 import os, sys
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 import torch
-from gaussianhaircut_b200 import losses as ghl
+from gaussianhaircut_b200 import _capi, losses as ghl
+if len(sys.argv) > 2:                               # development only: time a variant build of the library
+    _capi.LIB_PATH = os.path.abspath(sys.argv[2])
 dev = torch.device("cuda:0")
 W, H = 1920, 1080
 g = torch.Generator().manual_seed(3)
