@@ -17,6 +17,20 @@
 namespace {
 
 // ---------------------------------------------------------------- tile scan (1 block)
+// One CTA: exclusive scan of the per-tile histogram -> bucket cursors + tile ranges, the totals, and the launch
+// order of the blend kernels.  A single CTA lives on dependent latencies, so every tile count is loaded ONCE per
+// pass with two 128-bit loads per thread and all later phases work from registers.
+__device__ __forceinline__ void gh_load_counts8(const uint32_t* __restrict__ tile_count, int i0, int T, uint32_t (&c)[8]) {
+#pragma unroll
+    for (int k = 0; k < 8; k++) c[k] = 0u;
+    if (i0 + 8 <= T) {     // 32-byte aligned: two 128-bit loads
+        const uint4 a = reinterpret_cast<const uint4*>(tile_count + i0)[0], b = reinterpret_cast<const uint4*>(tile_count + i0)[1];
+        c[0] = a.x; c[1] = a.y; c[2] = a.z; c[3] = a.w; c[4] = b.x; c[5] = b.y; c[6] = b.z; c[7] = b.w;
+    } else {
+        for (int k = 0; k < 8; k++) if (i0 + k < T) c[k] = tile_count[i0 + k];
+    }
+}
+
 __global__ void __launch_bounds__(1024)
 gh_tile_scan_kernel(int T, const uint32_t* __restrict__ tile_count, uint32_t* __restrict__ tile_cursor,
                     uint2* __restrict__ ranges, uint32_t* __restrict__ tile_perm, GhCtrl* __restrict__ ctrl)
@@ -24,28 +38,40 @@ gh_tile_scan_kernel(int T, const uint32_t* __restrict__ tile_count, uint32_t* __
     // each thread owns 8 consecutive tiles per round: one block scan per 8192 tiles
     __shared__ uint32_t warp_sums[32], warp_max[32];
     __shared__ uint32_t carry_s;
+    // Launch order of the blend kernels: a counting sort of the tiles by list length, longest first
+    // (LPT scheduling: the ~14 waves of tile CTAs end together instead of waiting for a late heavy tile; the
+    // empty tiles, ~40% at the benchmark view, run last and only write background).  128 buckets of 16 records.
+    __shared__ uint32_t s_hist[128];
     const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
     if (tid == 0) carry_s = 0;
+    if (tid < 128) s_hist[tid] = 0u;
     uint32_t tmax = 0;
     __syncthreads();
     for (int base = 0; base < T; base += 8192) {
         const int i0 = base + tid * 8;
         uint32_t c[8];
+        gh_load_counts8(tile_count, i0, T, c);
         uint32_t sum = 0;
-#pragma unroll
-        for (int k = 0; k < 8; k++) c[k] = 0u;
-        if (i0 + 8 <= T) {     // 32-byte aligned: two 128-bit loads
-            const uint4 a = reinterpret_cast<const uint4*>(tile_count + i0)[0], b = reinterpret_cast<const uint4*>(tile_count + i0)[1];
-            c[0] = a.x; c[1] = a.y; c[2] = a.z; c[3] = a.w; c[4] = b.x; c[5] = b.y; c[6] = b.z; c[7] = b.w;
-        } else {
-            for (int k = 0; k < 8; k++) if (i0 + k < T) c[k] = tile_count[i0 + k];
-        }
 #pragma unroll
         for (int k = 0; k < 8; k++) { sum += c[k]; tmax = max(tmax, c[k]); }
         uint32_t v = sum;   // inclusive warp scan
 #pragma unroll
         for (int o = 1; o < 32; o <<= 1) { const uint32_t nb = __shfl_up_sync(0xffffffffu, v, o); if (lane >= o) v += nb; }
         if (lane == 31) warp_sums[wid] = v;
+        // histogram of list-length buckets.  Neighbouring tiles mostly share a bucket (the empty ones, ~40%, all
+        // do): a thread adds each RUN of equal buckets among its 8 tiles with one shared-memory atomic
+        {
+            int bkt[8];
+#pragma unroll
+            for (int k = 0; k < 8; k++) bkt[k] = (i0 + k < T) ? (int)(127u - min(127u, c[k] >> 4)) : -1;
+            uint32_t len = 0;
+#pragma unroll
+            for (int k = 0; k < 8; k++) {
+                len++;
+                const bool last = (k == 7) || (bkt[k + 1 < 8 ? k + 1 : 7] != bkt[k]);
+                if (last) { if (bkt[k] >= 0) atomicAdd(&s_hist[bkt[k]], len); len = 0; }
+            }
+        }
         __syncthreads();
         if (wid == 0) {
             uint32_t w = warp_sums[lane];
@@ -89,14 +115,6 @@ gh_tile_scan_kernel(int T, const uint32_t* __restrict__ tile_count, uint32_t* __
         ctrl->num_rendered = carry_s;
         ctrl->max_tile_len = m;
     }
-    // Launch order of the blend kernels: a counting sort of the tiles by list length, longest first
-    // (LPT scheduling: the ~14 waves of tile CTAs end together instead of waiting for a late heavy tile; the
-    // empty tiles, ~40% at the benchmark view, run last and only write background).  128 buckets of 16 records.
-    __shared__ uint32_t s_hist[128];
-    if (tid < 128) s_hist[tid] = 0u;
-    __syncthreads();
-    for (int i = tid; i < T; i += 1024) atomicAdd(&s_hist[127u - min(127u, tile_count[i] >> 4)], 1u);
-    __syncthreads();
     if (wid == 0) {      // exclusive scan of the 128 (descending-length) buckets: 4 per lane
         uint32_t c4[4], sum = 0;
 #pragma unroll
@@ -109,8 +127,29 @@ gh_tile_scan_kernel(int T, const uint32_t* __restrict__ tile_count, uint32_t* __
         for (int k = 0; k < 4; k++) { s_hist[lane * 4 + k] = run; run += c4[k]; }
     }
     __syncthreads();
-    for (int i = tid; i < T; i += 1024)
-        tile_perm[atomicAdd(&s_hist[127u - min(127u, tile_count[i] >> 4)], 1u)] = (uint32_t)i;
+    for (int base = 0; base < T; base += 8192) {
+        const int i0 = base + tid * 8;
+        uint32_t c[8];
+        gh_load_counts8(tile_count, i0, T, c);       // L1 / L2 hit
+        int bkt[8];
+        uint32_t rl[8], pos[8];
+#pragma unroll
+        for (int k = 0; k < 8; k++) bkt[k] = (i0 + k < T) ? (int)(127u - min(127u, c[k] >> 4)) : -1;
+        rl[7] = 1;
+#pragma unroll
+        for (int k = 6; k >= 0; k--) rl[k] = (bkt[k] == bkt[k + 1]) ? rl[k + 1] + 1 : 1;   // length of the run starting at k
+#pragma unroll
+        for (int k = 0; k < 8; k++) {
+            const bool first = (k == 0) || (bkt[k > 0 ? k - 1 : 0] != bkt[k]);
+            pos[k] = 0;
+            if (first && bkt[k] >= 0) pos[k] = atomicAdd(&s_hist[bkt[k]], rl[k]);     // independent reservations
+        }
+#pragma unroll
+        for (int k = 0; k < 8; k++) {
+            if (k > 0 && bkt[k - (k > 0 ? 1 : 0)] == bkt[k]) pos[k] = pos[k - (k > 0 ? 1 : 0)] + 1;
+            if (bkt[k] >= 0) tile_perm[pos[k]] = (uint32_t)(i0 + k);
+        }
+    }
 }
 
 // ---------------------------------------------------------------- emit
@@ -134,23 +173,21 @@ gh_emit_kernel(int P, const int* __restrict__ radii, const GhGeo* __restrict__ g
             rec = ((uint64_t)__float_as_uint(depth[idx]) << 32) | (uint32_t)idx;
         }
     }
-    const int w = maxx - minx;
-    const int count = w * (maxy - miny);
-    int maxcount = count;
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) maxcount = max(maxcount, __shfl_xor_sync(0xffffffffu, maxcount, o));
-    // GH_EMIT_U tiles per round: the slot reservations of a round are independent atomics, so their
-    // L2 round trips overlap instead of adding up
-    constexpr int GH_EMIT_U = 4;
-    int x = minx, y = miny;
-    for (int t0 = 0; t0 < maxcount; t0 += GH_EMIT_U) {
+    // the warp walks the flattened list of its (Gaussian, tile) instances, GH_EMIT_U x 32 items per round: the slot
+    // reservations of a round are independent atomics, so their L2 round trips overlap instead of adding up
+    const GhWarpRects wr = gh_warp_rects(minx, miny, maxx, maxy, lane);
+    const uint32_t rec_hi = (uint32_t)(rec >> 32);
+    const uint32_t idx0 = (uint32_t)(idx - lane);
+    constexpr int GH_EMIT_U = 2;
+    for (int j0 = 0; j0 < wr.total; j0 += 32 * GH_EMIT_U) {
         int tile[GH_EMIT_U];
-        uint32_t peers[GH_EMIT_U], base[GH_EMIT_U];
+        uint32_t peers[GH_EMIT_U], base[GH_EMIT_U], key_hi[GH_EMIT_U], key_lo[GH_EMIT_U];
 #pragma unroll
         for (int u = 0; u < GH_EMIT_U; u++) {
-            const bool have = t0 + u < count;
-            tile[u] = have ? (y * gx + x) : -1;
-            if (have && ++x == maxx) { x = minx; y++; }
+            int owner;
+            tile[u] = gh_warp_rect_item(wr, j0 + 32 * u + lane, gx, owner);
+            key_hi[u] = __shfl_sync(0xffffffffu, rec_hi, owner);
+            key_lo[u] = idx0 + (uint32_t)owner;
         }
 #pragma unroll
         for (int u = 0; u < GH_EMIT_U; u++) peers[u] = __match_any_sync(0xffffffffu, tile[u]);
@@ -162,10 +199,9 @@ gh_emit_kernel(int P, const int* __restrict__ radii, const GhGeo* __restrict__ g
         }
 #pragma unroll
         for (int u = 0; u < GH_EMIT_U; u++) {
-            if (tile[u] >= 0) {
-                const uint32_t b = __shfl_sync(peers[u], base[u], __ffs(peers[u]) - 1);
-                inst[b + __popc(peers[u] & ((1u << lane) - 1u))] = rec;
-            }
+            const uint32_t b = __shfl_sync(0xffffffffu, base[u], __ffs(peers[u]) - 1);
+            if (tile[u] >= 0)
+                inst[b + __popc(peers[u] & ((1u << lane) - 1u))] = ((uint64_t)key_hi[u] << 32) | key_lo[u];
         }
     }
 }

@@ -129,6 +129,46 @@ __device__ __forceinline__ void gh_get_rect(float px, float py, int radius, int 
     v = __float2int_rz(GH_MUL(GH_ADD(GH_ADD(GH_ADD(py, rf), 16.0f), -1.0f), 0.0625f)); maxy = min(gy, max(0, v));
 }
 
+// Warp-cooperative enumeration of the (Gaussian, tile) instances of a warp's 32 tile rectangles.  Splat rectangles
+// vary a lot in size (a strand segment seen end-on covers one tile, seen sideways a dozen), so a loop in which every
+// lane walks its own rectangle runs as long as the warp's LARGEST one; here the rectangles are flattened into one
+// list (warp prefix sum of their sizes) and lane l takes items l, l + 32, ...: ceil(sum / 32) rounds instead of max.
+struct GhWarpRects {
+    int incl, excl, w, minxy, total;
+    uint32_t rw;       // ceil(2^32 / w): k / w == umulhi(k, rw) for k * w < 2^32 (w >= 2)
+};
+__device__ __forceinline__ GhWarpRects gh_warp_rects(int minx, int miny, int maxx, int maxy, int lane) {
+    GhWarpRects r;
+    r.w = maxx - minx;
+    const int count = r.w * (maxy - miny);
+    int v = count;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) { const int nb = __shfl_up_sync(0xffffffffu, v, o); if (lane >= o) v += nb; }
+    r.incl = v; r.excl = v - count;
+    r.total = __shfl_sync(0xffffffffu, v, 31);
+    r.minxy = minx | (miny << 16);
+    r.rw = (r.w > 1) ? (0xffffffffu / (uint32_t)r.w + 1u) : 0u;
+    return r;
+}
+// item j of the flattened list: returns its tile (y * gx + x) and the lane that owns the rectangle, -1 past the end
+__device__ __forceinline__ int gh_warp_rect_item(const GhWarpRects& r, int j, int gx, int& owner) {
+    int lo = 0;     // number of lanes whose inclusive sum is <= j == first lane whose rectangle contains item j
+#pragma unroll
+    for (int s = 16; s > 0; s >>= 1) {
+        const int v = __shfl_sync(0xffffffffu, r.incl, lo + s - 1);
+        if (v <= j) lo += s;
+    }
+    owner = lo;
+    const int oexcl = __shfl_sync(0xffffffffu, r.excl, lo);
+    const int ow = __shfl_sync(0xffffffffu, r.w, lo);
+    const uint32_t orw = __shfl_sync(0xffffffffu, r.rw, lo);
+    const int oxy = __shfl_sync(0xffffffffu, r.minxy, lo);
+    const uint32_t k = (uint32_t)(j - oexcl);
+    const uint32_t q = (ow > 1) ? __umulhi(k, orw) : k;
+    const int x = (oxy & 0xffff) + (int)(k - q * (uint32_t)ow), y = (oxy >> 16) + (int)q;
+    return (j < r.total) ? y * gx + x : -1;
+}
+
 // World-space 3-D covariance from scale * modifier and a RAW (un-normalised) quaternion
 // (reference forward.cu:118-152; glm column-major products, see oracle/glm_shim).
 // Order of operations transcribed from the reference PTX.

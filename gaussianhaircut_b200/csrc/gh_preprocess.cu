@@ -163,25 +163,18 @@ gh_preprocess_kernel(int P,
         gp[1] = make_float4(g.cc, g.op, g.thr, g.pd);
     }
 
-    // per-tile histogram (replaces the reference's per-Gaussian tiles_touched + prefix sum).
-    // Neighbouring Gaussians of a strand hit the same tiles: lanes asking for the same tile in the same
-    // step are grouped with match.any and counted with one atomic.
+    // per-tile histogram (replaces the reference's per-Gaussian tiles_touched + prefix sum): the warp walks the
+    // flattened list of its (Gaussian, tile) instances (gh_warp_rects).  Neighbouring Gaussians of a strand hit the
+    // same tiles: lanes asking for the same tile in the same round are grouped with match.any and counted with one
+    // atomic.
     {
         const int lane = threadIdx.x & 31;
-        const int w = rect_maxx - rect_minx;
-        const int count = w * (rect_maxy - rect_miny);
-        int maxcount = count;
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) maxcount = max(maxcount, __shfl_xor_sync(0xffffffffu, maxcount, o));
-        int x = rect_minx, y = rect_miny;
-        for (int t = 0; t < maxcount; t++) {
-            const bool have = t < count;
-            const int tile = have ? (y * gx + x) : -1;
+        const GhWarpRects wr = gh_warp_rects(rect_minx, rect_miny, rect_maxx, rect_maxy, lane);
+        for (int j0 = 0; j0 < wr.total; j0 += 32) {
+            int owner;
+            const int tile = gh_warp_rect_item(wr, j0 + lane, gx, owner);
             const uint32_t peers = __match_any_sync(0xffffffffu, tile);
-            if (have) {
-                if (lane == __ffs(peers) - 1) atomicAdd(&tile_count[tile], (uint32_t)__popc(peers));
-                if (++x == rect_maxx) { x = rect_minx; y++; }
-            }
+            if (tile >= 0 && lane == __ffs(peers) - 1) atomicAdd(&tile_count[tile], (uint32_t)__popc(peers));
         }
     }
 }
