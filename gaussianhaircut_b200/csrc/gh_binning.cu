@@ -11,15 +11,23 @@
 //   4. each bucket is sorted in shared memory on the composite 64-bit (depth, idx) key, which
 //      reproduces the stable order because a Gaussian appears at most once per tile.
 // HBM traffic is 8 B write + 8 B read + 8 B write per instance instead of ~156 B for 6 radix passes.
+#include <cooperative_groups.h>
 #include "gh_common.cuh"
 #include "gh_kernels.h"
 
 namespace {
 
-// ---------------------------------------------------------------- tile scan (1 block)
-// One CTA: exclusive scan of the per-tile histogram -> bucket cursors + tile ranges, the totals, and the launch
-// order of the blend kernels.  A single CTA lives on dependent latencies, so every tile count is loaded ONCE per
-// pass with two 128-bit loads per thread and all later phases work from registers.
+// ---------------------------------------------------------------- tile scan (one cluster of 8 CTAs)
+// Exclusive scan of the per-tile histogram -> bucket cursors + tile ranges, the totals, and the launch order of
+// the blend kernels.  The problem is tiny (T = 8160 tiles at 1080p) and sits on the critical path between two
+// kernels, so what matters is latency and the store bandwidth of the SMs that take part: ONE thread-block cluster
+// of 8 CTAs (8 SMs) shares the work, exchanging CTA totals, bucket histograms and the maximum through distributed
+// shared memory instead of a second launch.  Every tile count is loaded once per pass with two 128-bit loads per
+// thread and all later phases work from registers.
+#define GH_SCAN_CTAS 8
+#define GH_SCAN_THREADS 256
+#define GH_SCAN_ROUND (GH_SCAN_CTAS * GH_SCAN_THREADS * 8)      // tiles per cluster round
+
 __device__ __forceinline__ void gh_load_counts8(const uint32_t* __restrict__ tile_count, int i0, int T, uint32_t (&c)[8]) {
 #pragma unroll
     for (int k = 0; k < 8; k++) c[k] = 0u;
@@ -31,24 +39,30 @@ __device__ __forceinline__ void gh_load_counts8(const uint32_t* __restrict__ til
     }
 }
 
-__global__ void __launch_bounds__(1024)
+__device__ __forceinline__ int gh_len_bucket(uint32_t count) { return (int)(127u - min(127u, count >> 4)); }
+
+__global__ void __cluster_dims__(GH_SCAN_CTAS, 1, 1) __launch_bounds__(GH_SCAN_THREADS)
 gh_tile_scan_kernel(int T, const uint32_t* __restrict__ tile_count, uint32_t* __restrict__ tile_cursor,
                     uint2* __restrict__ ranges, uint32_t* __restrict__ tile_perm, GhCtrl* __restrict__ ctrl)
 {
-    // each thread owns 8 consecutive tiles per round: one block scan per 8192 tiles
-    __shared__ uint32_t warp_sums[32], warp_max[32];
-    __shared__ uint32_t carry_s;
+    namespace cg = cooperative_groups;
+    cg::cluster_group cluster = cg::this_cluster();
+    constexpr int NW = GH_SCAN_THREADS / 32;
+    __shared__ uint32_t warp_sums[NW];
+    __shared__ uint32_t s_cta_total[2];         // this CTA's sum of the current round (double-buffered by round parity)
+    __shared__ uint32_t s_cta_max;
     // Launch order of the blend kernels: a counting sort of the tiles by list length, longest first
     // (LPT scheduling: the ~14 waves of tile CTAs end together instead of waiting for a late heavy tile; the
     // empty tiles, ~40% at the benchmark view, run last and only write background).  128 buckets of 16 records.
     __shared__ uint32_t s_hist[128];
     const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
-    if (tid == 0) carry_s = 0;
+    const unsigned rank = cluster.block_rank();
     if (tid < 128) s_hist[tid] = 0u;
-    uint32_t tmax = 0;
+    uint32_t tmax = 0, carry = 0;
     __syncthreads();
-    for (int base = 0; base < T; base += 8192) {
-        const int i0 = base + tid * 8;
+    int round = 0;
+    for (int base = 0; base < T; base += GH_SCAN_ROUND, round++) {
+        const int i0 = base + ((int)rank * GH_SCAN_THREADS + tid) * 8;
         uint32_t c[8];
         gh_load_counts8(tile_count, i0, T, c);
         uint32_t sum = 0;
@@ -63,7 +77,7 @@ gh_tile_scan_kernel(int T, const uint32_t* __restrict__ tile_count, uint32_t* __
         {
             int bkt[8];
 #pragma unroll
-            for (int k = 0; k < 8; k++) bkt[k] = (i0 + k < T) ? (int)(127u - min(127u, c[k] >> 4)) : -1;
+            for (int k = 0; k < 8; k++) bkt[k] = (i0 + k < T) ? gh_len_bucket(c[k]) : -1;
             uint32_t len = 0;
 #pragma unroll
             for (int k = 0; k < 8; k++) {
@@ -73,15 +87,20 @@ gh_tile_scan_kernel(int T, const uint32_t* __restrict__ tile_count, uint32_t* __
             }
         }
         __syncthreads();
-        if (wid == 0) {
-            uint32_t w = warp_sums[lane];
+        uint32_t before = 0, cta_sum = 0;          // sum of the warps before mine / of the CTA
 #pragma unroll
-            for (int o = 1; o < 32; o <<= 1) { const uint32_t nb = __shfl_up_sync(0xffffffffu, w, o); if (lane >= o) w += nb; }
-            warp_sums[lane] = w;   // inclusive over warps
+        for (int w = 0; w < NW; w++) { const uint32_t ws = warp_sums[w]; before += (w < wid) ? ws : 0u; cta_sum += ws; }
+        if (tid == 0) s_cta_total[round & 1] = cta_sum;
+        cluster.sync();                            // totals of all 8 CTAs visible (also orders the warp_sums reuse)
+        uint32_t cta_before = 0, round_sum = 0;
+#pragma unroll
+        for (unsigned r = 0; r < GH_SCAN_CTAS; r++) {
+            const uint32_t t = cluster.map_shared_rank(s_cta_total, r)[round & 1];
+            cta_before += (r < rank) ? t : 0u;
+            round_sum += t;
         }
-        __syncthreads();
-        const uint32_t carry = carry_s;
-        uint32_t run = carry + (v - sum) + (wid > 0 ? warp_sums[wid - 1] : 0u);
+        uint32_t run = carry + cta_before + before + (v - sum);
+        carry += round_sum;
         uint32_t cur8[8];
         uint2 rg8[8];
 #pragma unroll
@@ -101,40 +120,57 @@ gh_tile_scan_kernel(int T, const uint32_t* __restrict__ tile_count, uint32_t* __
         } else {
             for (int k = 0; k < 8; k++) if (i0 + k < T) { tile_cursor[i0 + k] = cur8[k]; ranges[i0 + k] = rg8[k]; }
         }
-        __syncthreads();
-        if (tid == 1023) carry_s = run;
-        __syncthreads();
     }
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) tmax = max(tmax, __shfl_xor_sync(0xffffffffu, tmax, o));
-    if (lane == 0) warp_max[wid] = tmax;
+    if (lane == 0) warp_sums[wid] = tmax;          // (every thread is past the last round's cluster.sync)
     __syncthreads();
     if (tid == 0) {
         uint32_t m = 0;
-        for (int w = 0; w < 32; w++) m = max(m, warp_max[w]);
-        ctrl->num_rendered = carry_s;
+        for (int w = 0; w < NW; w++) m = max(m, warp_sums[w]);
+        s_cta_max = m;
+    }
+    cluster.sync();                                // histograms and maxima of all CTAs complete
+    if (rank == 0 && tid == 0) {
+        uint32_t m = 0;
+        for (unsigned r = 0; r < GH_SCAN_CTAS; r++) m = max(m, *cluster.map_shared_rank(&s_cta_max, r));
+        ctrl->num_rendered = carry;
         ctrl->max_tile_len = m;
     }
-    if (wid == 0) {      // exclusive scan of the 128 (descending-length) buckets: 4 per lane
-        uint32_t c4[4], sum = 0;
+    // first slot of (bucket, this CTA) in the permutation: buckets in descending-length order, CTAs by rank inside
+    uint32_t mine_before = 0, bucket_total = 0;
+    if (tid < 128) {
 #pragma unroll
-        for (int k = 0; k < 4; k++) { c4[k] = s_hist[lane * 4 + k]; sum += c4[k]; }
-        uint32_t v = sum;
+        for (unsigned r = 0; r < GH_SCAN_CTAS; r++) {
+            const uint32_t h = cluster.map_shared_rank(s_hist, r)[tid];
+            mine_before += (r < rank) ? h : 0u;
+            bucket_total += h;
+        }
+    }
+    cluster.sync();                                // everyone has read the histograms: they become cursors now
+    if (tid < 128) {                               // exclusive scan of the 128 bucket totals (4 warps)
+        uint32_t v = bucket_total;
 #pragma unroll
         for (int o = 1; o < 32; o <<= 1) { const uint32_t nb = __shfl_up_sync(0xffffffffu, v, o); if (lane >= o) v += nb; }
-        uint32_t run = v - sum;
-#pragma unroll
-        for (int k = 0; k < 4; k++) { s_hist[lane * 4 + k] = run; run += c4[k]; }
+        if (lane == 31) warp_sums[wid] = v;
+        s_hist[tid] = v - bucket_total + mine_before;
     }
     __syncthreads();
-    for (int base = 0; base < T; base += 8192) {
-        const int i0 = base + tid * 8;
+    if (tid < 128) {
+        uint32_t before = 0;
+#pragma unroll
+        for (int w = 0; w < 4; w++) before += (w < wid) ? warp_sums[w] : 0u;
+        s_hist[tid] += before;
+    }
+    __syncthreads();
+    for (int base = 0; base < T; base += GH_SCAN_ROUND) {
+        const int i0 = base + ((int)rank * GH_SCAN_THREADS + tid) * 8;
         uint32_t c[8];
         gh_load_counts8(tile_count, i0, T, c);       // L1 / L2 hit
         int bkt[8];
         uint32_t rl[8], pos[8];
 #pragma unroll
-        for (int k = 0; k < 8; k++) bkt[k] = (i0 + k < T) ? (int)(127u - min(127u, c[k] >> 4)) : -1;
+        for (int k = 0; k < 8; k++) bkt[k] = (i0 + k < T) ? gh_len_bucket(c[k]) : -1;
         rl[7] = 1;
 #pragma unroll
         for (int k = 6; k >= 0; k--) rl[k] = (bkt[k] == bkt[k + 1]) ? rl[k + 1] + 1 : 1;   // length of the run starting at k
@@ -306,7 +342,7 @@ gh_segment_sort_kernel(const uint2* __restrict__ seg, const GhCtrl* __restrict__
 
 void gh_launch_tile_scan(int T, GhImgWS img, cudaStream_t stream)
 {
-    gh_tile_scan_kernel<<<1, 1024, 0, stream>>>(T, img.tile_count, img.tile_cursor, img.ranges, img.tile_perm, img.ctrl);
+    gh_tile_scan_kernel<<<GH_SCAN_CTAS, GH_SCAN_THREADS, 0, stream>>>(T, img.tile_count, img.tile_cursor, img.ranges, img.tile_perm, img.ctrl);
 }
 
 void gh_launch_emit(int P, const int* radii, GhGeomWS geom, GhImgWS img, GhBinWS bin,
