@@ -643,9 +643,12 @@ __device__ __forceinline__ bool gh_bwd_pair(GhBwdPair& p, const float4 g0, const
     // alpha also scales how much background shows through (backward.cu:535-538).  Not masked: every use
     // below is multiplied by G, which is 0 for a pixel that does not blend.
     const float2 dL_dalpha = gh_fma2(gh_sub2(cdot, A_new), p.T, gh_mul2(p.ntf_bg, r));
-    p.A = make_float2(ok0 ? A_new.x : p.A.x, ok1 ? A_new.y : p.A.y);
-    p.last_cdot = make_float2(ok0 ? cdot.x : p.last_cdot.x, ok1 ? cdot.y : p.last_cdot.y);
-    p.last_alpha = make_float2(ok0 ? alpha0 : p.last_alpha.x, ok1 ? alpha1 : p.last_alpha.y);
+    // State update WITHOUT selects: a pixel that does not blend stores last_alpha = 0, so the next step computes
+    // A_new = fma(0, last_cdot, 1 * A) = A exactly (cdot is finite) -- the recursion skips it just as the
+    // reference's `continue` does, and A_new of this step is what the next blended step would have computed.
+    p.A = A_new;
+    p.last_cdot = cdot;
+    p.last_alpha = am;
     const float2 dL_dG = gh_mul2(gh_f2(g1.y), dL_dalpha);
     const float2 gdx = gh_mul2(G, dx2), gdy = gh_mul2(G, dy);
     const float2 ncb = gh_f2(-g0.w);

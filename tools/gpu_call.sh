@@ -1,6 +1,7 @@
 #!/bin/bash
 mkdir -p gpurun_out
-python -m pytest tests/test_gpu_parity.py tests/test_gpu_reference_callers.py -m gpu -x -q 2>&1 | tail -3 > gpurun_out/pytest_gpu.txt
-python tools/stage_times.py > gpurun_out/stage_times.txt 2>&1
-python tools/stage_times.py --strands 20000 >> gpurun_out/stage_times.txt 2>&1
-cat gpurun_out/pytest_gpu.txt; cat gpurun_out/stage_times.txt | tail -4
+bash tools/profile_round.sh r02_final > gpurun_out/r02_final_round.log 2>&1
+python tools/train_loop.py --strands 20000 --iters 300 2>/dev/null | tail -1 > gpurun_out/r02_final_config5_mine.json
+python tools/train_loop.py --strands 5000 --iters 300 2>/dev/null | tail -1 > gpurun_out/r02_final_config4shape_mine.json
+tail -30 gpurun_out/r02_final_round.log
+cat gpurun_out/r02_final_config5_mine.json gpurun_out/r02_final_config4shape_mine.json | cut -c1-600
