@@ -186,6 +186,12 @@ def main():
 
     for it in range(args.warmup):
         iteration(-1000 + it)                   # negative counters never hit a densification boundary
+    if use_dist and args.impl == "mine" and not args.no_densify:
+        # NCCL sets up the connections of an algorithm / protocol the first time a collective of that size class runs
+        # (0.4 s at 2 GPUs, 1.5 s at 8, measured): a one-time cost of a 30 000-iteration run that would otherwise be
+        # charged to the first densification of this 300-iteration window
+        from gaussianhaircut_b200 import dist as _ghd
+        _ghd.allreduce_densification_stats(torch.zeros_like(pc.xyz_gradient_accum), torch.zeros_like(pc.denom), torch.zeros_like(pc.max_radii2D))
     sizes.clear()
     timing["on"] = True
     sync()
