@@ -65,6 +65,24 @@ def _pool_alloc(gaussians, key: str, rows: int, tail, dev, avoid: Optional[torch
     return b[:need].view((rows,) + tuple(int(d) for d in tail))
 
 
+def reserve_pools(gaussians, rows: int) -> None:
+    """Allocate both pooled buffers of every tensor that densification rebuilds (parameters and Adam moments) for a
+    model of up to `rows` Gaussians, so that no densification of the run has to go to cudaMalloc.  Optional: without it
+    the pools are created by the first two calls of `densify_and_prune` -- which costs ~0.1 s per call at 2 M Gaussians
+    on one GPU and ~1.5 s once NCCL has enabled peer access between 8 GPUs (every cudaMalloc then maps the block into
+    all peers), measured with tools/train_loop.py."""
+    opt = gaussians.optimizer
+    dev = gaussians._xyz.device
+    for group in opt.param_groups:
+        name = group.get("name")
+        if name not in GROUPS:
+            continue
+        p = group["params"][0]
+        for key in (name, name + ".exp_avg", name + ".exp_avg_sq"):
+            a = _pool_alloc(gaussians, key, rows, p.shape[1:], dev, None)
+            _pool_alloc(gaussians, key, rows, p.shape[1:], dev, a)
+
+
 def classify(gaussians, max_grad: float, min_opacity: float, extent: float, max_screen_size) -> torch.Tensor:
     """(P,4) int32 flags: [original survives, its clone survives, its two children survive, it is split]."""
     lib = _capi.load()

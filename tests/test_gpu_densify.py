@@ -112,6 +112,35 @@ def test_densify_and_prune_matches_the_reference(cuda_device, n, max_screen_size
         assert rel_err(grp_b["params"][0].detach(), grp_a["params"][0].detach()) <= 1e-6, grp_a["name"]
 
 
+def test_reserved_pools_are_used_and_change_nothing(cuda_device):
+    """densify.reserve_pools: the rebuilt tensors live in the buffers allocated up front (no allocation inside the
+    call), results identical to the un-reserved path."""
+    from gaussianhaircut_b200 import densify
+    scene = _scene(20000, seed=3)
+    a = _model(scene, cuda_device, True, fused=True, seed=7)
+    b = _model(scene, cuda_device, True, fused=True, seed=7)
+    densify.reserve_pools(b, 400000)
+    slots = {k: [t.data_ptr() for t in v] for k, v in b._gh_pools.items()}
+    assert all(len(v) == 2 and v[0] != v[1] for v in slots.values()) and len(slots) == 3 * 8
+    for rnd in range(3):                                   # source and destination alternate between the two slots
+        for pc in (a, b):
+            torch.manual_seed(5 + rnd); torch.cuda.manual_seed(5 + rnd)
+            P = pc._xyz.shape[0]
+            g = torch.Generator().manual_seed(rnd)
+            pc.xyz_gradient_accum = (torch.rand(P, 1, generator=g) * 6e-4).to(cuda_device)
+            pc.denom = torch.randint(1, 3, (P, 1), generator=g).float().to(cuda_device)
+            densify.densify_and_prune(pc, 2e-4, 0.005, 2.0, 20)
+        assert a._xyz.shape == b._xyz.shape
+        for name in NAMES:
+            pa = [g for g in a.optimizer.param_groups if g["name"] == name][0]["params"][0]
+            pb = [g for g in b.optimizer.param_groups if g["name"] == name][0]["params"][0]
+            assert torch.equal(pa.detach(), pb.detach()), name
+            assert torch.equal(a.optimizer.state[pa]["exp_avg_sq"], b.optimizer.state[pb]["exp_avg_sq"]), name
+            assert pb.data_ptr() in slots[name], name      # still inside the reserved buffers
+            assert b.optimizer.state[pb]["exp_avg"].data_ptr() in slots[name + ".exp_avg"], name
+    assert {k: [t.data_ptr() for t in v] for k, v in b._gh_pools.items()} == slots
+
+
 def test_reset_opacity_matches_the_reference(cuda_device):
     from gaussianhaircut_b200 import densify
     scene = _scene(5000, seed=5)

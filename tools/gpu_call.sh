@@ -1,7 +1,6 @@
 #!/bin/bash
 mkdir -p gpurun_out
-TR="python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1"
-timeout 300 $TR --master-port 29512 tools/train_loop.py --strands 20000 --iters 300 --profile 2>/dev/null | tail -1 > gpurun_out/prof_config5_2gpu.json
-timeout 300 python tools/train_loop.py --strands 20000 --iters 300 --profile 2>/dev/null | tail -1 > gpurun_out/prof_config5_1gpu.json
-timeout 300 $TR --master-port 29513 tools/train_loop.py --strands 20000 --iters 300 2>/dev/null | tail -1 > gpurun_out/config5_2gpu.json
-cut -c1-1500 gpurun_out/prof_config5_2gpu.json gpurun_out/prof_config5_1gpu.json gpurun_out/config5_2gpu.json
+TR="python -m torch.distributed.run --nnodes=1 --nproc-per-node 8 --master-addr 127.0.0.1"
+GH_DENSIFY_PROFILE=1 timeout 300 $TR --master-port 29512 tools/train_loop.py --strands 20000 --iters 300 2> gpurun_out/c5_8gpu.err | tail -1 > gpurun_out/r02_final_config5_mine_8gpu.json
+grep "densify\]" gpurun_out/c5_8gpu.err | sort | uniq -c | sort -k2 | head -40
+cut -c1-600 gpurun_out/r02_final_config5_mine_8gpu.json

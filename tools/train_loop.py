@@ -101,6 +101,8 @@ def main():
             projection.set_gradient_arena(par.buffer)
         pipe = types.SimpleNamespace(debug=False)
         order = ("xyz", "f_dc", "f_rest", "opacity", "label", "scaling", "rotation", "conf")
+        if not args.no_densify:
+            densify.reserve_pools(pc, int(P0 * 1.1))      # like the arena: sized once for the run, no cudaMalloc in the loop
 
         def iteration(it):
             cam = cams[(it * world + rank) % len(cams)]
