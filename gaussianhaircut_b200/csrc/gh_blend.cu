@@ -440,6 +440,7 @@ __device__ __forceinline__ void gh_stage_issue_b(GhStageB& st, int slot, uint32_
 // them would take the reference's `alpha < 1/255 -> continue` (forward.cu:370, backward.cu:503).
 // Two pixel rows per instruction; a row without a real span has disc <= 0 -> s = NaN -> fminf / fmaxf
 // ignore it.
+#if GH_BWD_LPB == 4      // (the 4x2-block variant of the measured A/B; the product builds 2x2)
 __device__ __forceinline__ uint32_t gh_block_mask2(const float4 g0, const float4 g1, float tx0, float ty0) {
     const float gx = g0.x, gy = g0.y, a = g0.z, b = g0.w, c = g1.x, thr = g1.z, pd = g1.w;
     if (pd == 0.f) return 0xffffffffu;
@@ -470,8 +471,10 @@ __device__ __forceinline__ uint32_t gh_block_mask2(const float4 g0, const float4
     }
     return mask;
 }
+#endif
 
 // The same test at 2x2-block granularity: 64 blocks, bit = by * 8 + bx; .x = block rows 0..3, .y = rows 4..7.
+#if GH_BWD_LPB != 4
 __device__ __forceinline__ uint2 gh_block_mask_2x2(const float4 g0, const float4 g1, float tx0, float ty0) {
     const float gx = g0.x, gy = g0.y, a = g0.z, b = g0.w, c = g1.x, thr = g1.z, pd = g1.w;
     if (pd == 0.f) return make_uint2(0xffffffffu, 0xffffffffu);
@@ -500,6 +503,7 @@ __device__ __forceinline__ uint2 gh_block_mask_2x2(const float4 g0, const float4
     }
     return make_uint2(m[0], m[1]);
 }
+#endif
 
 // batch `word` = instances [32 word, 32 word + 32) of the window, one per lane; a 5-step shuffle
 // transpose turns the 32 block masks into one list word per block (lane = block).  The word is cut at
@@ -544,6 +548,7 @@ __device__ __forceinline__ void gh_build_lists_b(GhStageB& st, int cnt, int word
 // is 80 B (16 floats + pad): the 8 lanes of a quarter-warp store to, and load from, 8 disjoint groups
 // of 4 banks.
 #define GH_RED_STRIDE4 5       // float4 per lane record
+#if GH_BWD_LPB == 4
 __device__ __forceinline__ float4 gh_group4_reduce16(const float (&v)[16], float4* warp_buf, int lane) {
     float4* mine = warp_buf + lane * GH_RED_STRIDE4;
     mine[0] = make_float4(v[0], v[1], v[2], v[3]);
@@ -560,11 +565,13 @@ __device__ __forceinline__ float4 gh_group4_reduce16(const float (&v)[16], float
                               gh_add2(make_float2(c.z, c.w), make_float2(d.z, d.w)));
     return make_float4(lo.x, lo.y, hi.x, hi.y);
 }
+#endif
 
 // 2-lane blocks: the even lane keeps components 0..7, the odd lane 8..15 (two REDG.E.ADD.F32x4 each).  Each lane
 // stores the half its partner keeps (2 STS.128), loads the partner's contribution to its own half (2 LDS.128) and
 // adds (4 FADD2).  Record stride 48 B: the 8 lanes of a quarter-warp hit 8 disjoint groups of 4 banks.
 #define GH_RED2_STRIDE4 3
+#if GH_BWD_LPB != 4
 __device__ __forceinline__ void gh_group2_reduce16(const float (&v)[16], float4* warp_buf, int lane, float4& out0, float4& out1) {
     const bool odd = (lane & 1) != 0;
     float4* mine = warp_buf + lane * GH_RED2_STRIDE4;
@@ -582,6 +589,7 @@ __device__ __forceinline__ void gh_group2_reduce16(const float (&v)[16], float4*
     out0 = make_float4(s0.x, s0.y, s1.x, s1.y);
     out1 = make_float4(s2.x, s2.y, s3.x, s3.y);
 }
+#endif
 
 // State of the lane's pixel pair; .x = pixel (x, y0), .y = pixel (x, y0 + 1).
 struct GhBwdPair {
