@@ -213,7 +213,10 @@ __device__ __forceinline__ void gh_build_pixel_lists(const GhStage& st, uint32_t
 }
 
 // ------------------------------------------------------------------------------------------ forward
-__global__ void __launch_bounds__(256, 4)
+#ifndef GH_FWD_MIN_CTAS
+#define GH_FWD_MIN_CTAS 4        // __launch_bounds__ second argument of the forward kernel (register cap)
+#endif
+__global__ void __launch_bounds__(256, GH_FWD_MIN_CTAS)
 gh_blend_forward_kernel(const uint2* __restrict__ ranges, const uint32_t* __restrict__ tile_perm, uint64_t* inst,
                         const GhGeo* __restrict__ geo, const float* __restrict__ features,
                         int W, int H, int gx, const float* __restrict__ bg,

@@ -1,6 +1,5 @@
 #!/bin/bash
 mkdir -p gpurun_out
-python -m pytest tests -m gpu -x -q 2>&1 | tail -3 > gpurun_out/r02_final_pytest_gpu.txt
-python -c "import __graft_entry__ as g; g.smoke(); print('smoke ok')" 2>&1 | tail -2
-python bench.py --no-cpu-baseline 2>/dev/null | tail -1 | cut -c1-400
-cat gpurun_out/r02_final_pytest_gpu.txt
+python tools/bench_variants.py run > gpurun_out/fwd_variants.txt 2>&1
+python tools/bench_variants.py run --strands 20000 >> gpurun_out/fwd_variants.txt 2>&1
+grep -v "^\[" gpurun_out/fwd_variants.txt
