@@ -147,6 +147,42 @@ def rasterize_gaussians(
     return R, out_color, radii, geomBuffer, binningBuffer, imgBuffer
 
 
+def alloc_forward_workspaces(P: int, W: int, H: int, device: torch.device):
+    """(geomBuffer, imgBuffer, radii) of a forward pass -- what rasterize_gaussians allocates before its first native
+    call; used by the fused projection (projection.project_forward_binned), which fills them itself."""
+    lib = _capi.load()
+    byte_opts = dict(dtype=torch.uint8, device=device)
+    geom_bytes, img_bytes, geom_cap = C.c_size_t(), C.c_size_t(), C.c_size_t()
+    _capi.check(lib.gh_forward_workspace_sizes(P, W, H, C.byref(geom_bytes), C.byref(img_bytes)))
+    _capi.check(lib.gh_forward_workspace_sizes(row_capacity(P), W, H, C.byref(geom_cap), None))
+    geomBuffer = torch.empty(geom_cap.value, **byte_opts)[:geom_bytes.value]
+    imgBuffer = torch.empty(img_bytes.value, **byte_opts)
+    radii = empty_rows(P, (), torch.int32, device)
+    return geomBuffer, imgBuffer, radii
+
+
+def forward_render(background: torch.Tensor, colors: torch.Tensor, radii: torch.Tensor, geomBuffer: torch.Tensor,
+                   imgBuffer: torch.Tensor, num_rendered: int, max_tile_len: int, image_height: int, image_width: int,
+                   debug: bool = False):
+    """Second phase of the forward (emit, sort, blend) on workspaces whose first phase already ran
+    (gh_forward_preprocess or gh_project_forward_binned).  -> (out_color (C,H,W), binningBuffer)."""
+    lib = _capi.load()
+    device = colors.device
+    P, H, W = int(colors.shape[0]), int(image_height), int(image_width)
+    with torch.cuda.device(device):
+        background = _prep(background, "background", device)
+        colors = _prep(colors, "colors", device, align=8)
+        out_color = torch.empty((NUM_CHANNELS, H, W), dtype=torch.float32, device=device)
+        bin_bytes = C.c_size_t()
+        _capi.check(lib.gh_binning_workspace_size(int(num_rendered), C.byref(bin_bytes)))
+        binningBuffer = torch.empty(bin_bytes.value, dtype=torch.uint8, device=device)
+        _capi.check(lib.gh_forward_render(
+            P, W, H, _ptr(background), _ptr(colors), _ptr(radii),
+            _ptr(geomBuffer), _ptr(binningBuffer), _ptr(imgBuffer),
+            int(num_rendered), int(max_tile_len), _ptr(out_color), int(bool(debug)), _stream(device)))
+    return out_color, binningBuffer
+
+
 def alloc_grad_arena(P: int, device: torch.device, zero: bool = True, storage: torch.Tensor | None = None):
     """One flat float32 buffer holding all per-Gaussian gradients + named (P, n) views.
     `zero=False` skips the fill: gh_backward writes every element itself.  `storage`: use (the head of)

@@ -18,7 +18,7 @@ GH_E_NO_COLORS = 2
 GH_E_CUDA = 3
 GH_E_PREFILTERED = 4
 
-ABI_VERSION = 2
+ABI_VERSION = 3
 
 _p = C.c_void_p
 _i = C.c_int
@@ -78,6 +78,16 @@ SIGNATURES = {
         _f, _f, _f, _i, C.c_uint, _f,        # tan_fovx tan_fovy scale_modifier sh_degree flags det_eps
         _p, _p, _p, _p, _p, _p,              # means2D colors opacities conic cov3D visible
         _p]),                                # stream
+    "gh_project_forward_binned": (_i, [
+        _i, _i, _i,
+        _p, _p, _p, _p,
+        _p, _p,
+        _p, _p, _p,
+        _p, _p, _p,
+        _f, _f, _f, _i, C.c_uint, _f,
+        _p, _p, _p, _p, _p, _p,              # means2D colors opacities conic cov3D visible
+        _p, _p, _p, C.POINTER(C.c_int), C.POINTER(C.c_int),   # radii geom_buffer img_buffer num_rendered max_tile_len
+        _p]),
     "gh_project_backward": (_i, [
         _i, _i, _i,
         _p, _p, _p, _p,

@@ -106,7 +106,7 @@ void gh_count_launches(int n) { g_launches.fetch_add((unsigned long long)n); }
 
 extern "C" {
 
-int gh_abi_version(void) { return 2; }
+int gh_abi_version(void) { return 3; }
 
 unsigned long long gh_kernel_launch_count(void) { return g_launches.load(); }
 

@@ -129,6 +129,71 @@ __device__ __forceinline__ void gh_get_rect(float px, float py, int radius, int 
     v = __float2int_rz(GH_MUL(GH_ADD(GH_ADD(GH_ADD(py, rf), 16.0f), -1.0f), 0.0625f)); maxy = min(gy, max(0, v));
 }
 
+// ---- stage-1 pieces shared by gh_preprocess_kernel and the fused projection kernel (gh_project.cu) -------------
+__device__ __forceinline__ float gh_ndc2pix(float v, int S) {
+    // auxiliary.h:41-44: ((v + 1.0) * S - 1.0) * 0.5 with double literals -> evaluated in FP64
+    double t = __dadd_rn((double)v, 1.0);
+    t = __fma_rn(t, (double)S, -1.0);
+    t = __dmul_rn(t, 0.5);
+    return __double2float_rn(t);
+}
+
+// View-space depth + near cull (auxiliary.h:154) and the NDC projection (forward.cu:201-206).  false = culled.
+__device__ __forceinline__ bool gh_pre_project(float px, float py, float pz, const float* __restrict__ vm,
+                                               const float* __restrict__ pm, float& zview, float& projx, float& projy) {
+    zview = GH_ADD(__ldg(vm + 14), GH_FMA(pz, __ldg(vm + 10), GH_FMA(px, __ldg(vm + 2), GH_MUL(py, __ldg(vm + 6)))));
+    if (zview <= 0.2f) return false;
+    const float hx = GH_ADD(__ldg(pm + 12), GH_FMA(pz, __ldg(pm + 8), GH_FMA(px, __ldg(pm + 0), GH_MUL(py, __ldg(pm + 4)))));
+    const float hy = GH_ADD(__ldg(pm + 13), GH_FMA(pz, __ldg(pm + 9), GH_FMA(px, __ldg(pm + 1), GH_MUL(py, __ldg(pm + 5)))));
+    const float hw = GH_ADD(__ldg(pm + 15), GH_FMA(pz, __ldg(pm + 11), GH_FMA(px, __ldg(pm + 3), GH_MUL(py, __ldg(pm + 7)))));
+    const float p_w = GH_RCP(GH_ADD(hw, 0.0000001f));
+    projx = GH_MUL(hx, p_w); projy = GH_MUL(hy, p_w);
+    return true;
+}
+
+// Caller-supplied conic: invert it to size the splat (forward.cu:238-248).  false = singular (not rendered).
+__device__ __forceinline__ bool gh_pre_from_conic(float conx, float cony, float conz, float& covx, float& covz, float& det) {
+    const float det_inv = GH_FMA(conx, conz, -GH_MUL(cony, cony));
+    if (det_inv == 0.0f) return false;
+    det = GH_RCP(det_inv);
+    covx = GH_MUL(conz, det);
+    covz = GH_MUL(conx, det);
+    return true;
+}
+
+// Splat extent from the larger eigenvalue (forward.cu:254-257), pixel centre, tile rectangle and the 32-byte state
+// record of the blend kernels.  Returns the radius (0 = not rendered; rect and g are then left untouched).
+__device__ __forceinline__ int gh_pre_finish(float covx, float covz, float det, float conx, float cony, float conz,
+                                             float projx, float projy, float op, int W, int H, int gx, int gy,
+                                             int& minx, int& miny, int& maxx, int& maxy, GhGeo& g) {
+    const float mid = GH_MUL(GH_ADD(covx, covz), 0.5f);
+    const float sq = GH_SQRT(fmaxf(GH_FMA(mid, mid, -det), 0.1f));
+    const float lam = fmaxf(GH_ADD(mid, sq), GH_SUB(mid, sq));
+    const float my_radius = ceilf(GH_MUL(GH_SQRT(lam), 3.0f));
+    const float pix_x = gh_ndc2pix(projx, W), pix_y = gh_ndc2pix(projy, H);
+    const int ri = __float2int_rz(my_radius);
+    // NaN covariance -> NaN radius -> 0: the reference counts such a Gaussian in tiles_touched but never
+    // emits its key (duplicateWithKeys tests radii > 0), leaving an uninitialised record in the list;
+    // dropping it here keeps the histogram and the emit consistent
+    if (ri <= 0) return 0;
+    int x0, y0, x1, y1;
+    gh_get_rect(pix_x, pix_y, ri, gx, gy, x0, y0, x1, y1);
+    if ((x1 - x0) * (y1 - y0) == 0) return 0;
+    g.x = pix_x; g.y = pix_y; g.ca = conx; g.cb = cony; g.cc = conz; g.op = op;
+    g.thr = __logf(255.0f * op);           // only used by the conservative cull (slack covers the approx)
+    g.thr = (255.0f * op > 0.f) ? g.thr : -1e30f;
+    const bool pd = (conx > 0.f) && (conz > 0.f) && (conx * conz - cony * cony > 0.f) && (op == op);
+    g.pd = pd ? 1.0f : 0.0f;
+    if (!(op == op)) g.thr = 1e30f;        // NaN opacity blends with alpha 0.99 in the reference (min.f32)
+    minx = x0; miny = y0; maxx = x1; maxy = y1;
+    return ri;
+}
+
+__device__ __forceinline__ GhGeo gh_geo_not_rendered() {
+    GhGeo g; g.x = 0.f; g.y = 0.f; g.ca = 0.f; g.cb = 0.f; g.cc = 0.f; g.op = 0.f; g.thr = -1e30f; g.pd = 0.f;
+    return g;
+}
+
 // Warp-cooperative enumeration of the (Gaussian, tile) instances of a warp's 32 tile rectangles.  Splat rectangles
 // vary a lot in size (a strand segment seen end-on covers one tile, seen sideways a dozen), so a loop in which every
 // lane walks its own rectangle runs as long as the warp's LARGEST one; here the rectangles are flattened into one
@@ -167,6 +232,22 @@ __device__ __forceinline__ int gh_warp_rect_item(const GhWarpRects& r, int j, in
     const uint32_t q = (ow > 1) ? __umulhi(k, orw) : k;
     const int x = (oxy & 0xffff) + (int)(k - q * (uint32_t)ow), y = (oxy >> 16) + (int)q;
     return (j < r.total) ? y * gx + x : -1;
+}
+
+// per-tile histogram of a warp's rectangles (replaces the reference's per-Gaussian tiles_touched + prefix sum): the
+// warp walks the flattened list of its (Gaussian, tile) instances.  Neighbouring Gaussians of a strand hit the same
+// tiles: lanes asking for the same tile in the same round are grouped with match.any and counted with one atomic.
+// Must be called by all 32 lanes (empty rectangle = nothing to count).
+__device__ __forceinline__ void gh_warp_tile_histogram(int minx, int miny, int maxx, int maxy, int gx,
+                                                       uint32_t* __restrict__ tile_count) {
+    const int lane = threadIdx.x & 31;
+    const GhWarpRects wr = gh_warp_rects(minx, miny, maxx, maxy, lane);
+    for (int j0 = 0; j0 < wr.total; j0 += 32) {
+        int owner;
+        const int tile = gh_warp_rect_item(wr, j0 + lane, gx, owner);
+        const uint32_t peers = __match_any_sync(0xffffffffu, tile);
+        if (tile >= 0 && lane == __ffs(peers) - 1) atomicAdd(&tile_count[tile], (uint32_t)__popc(peers));
+    }
 }
 
 // World-space 3-D covariance from scale * modifier and a RAW (un-normalised) quaternion

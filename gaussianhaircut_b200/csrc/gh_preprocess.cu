@@ -11,14 +11,6 @@
 
 namespace {
 
-__device__ __forceinline__ float gh_ndc2pix(float v, int S) {
-    // auxiliary.h:41-44: ((v + 1.0) * S - 1.0) * 0.5 with double literals -> evaluated in FP64
-    double t = __dadd_rn((double)v, 1.0);
-    t = __fma_rn(t, (double)S, -1.0);
-    t = __dmul_rn(t, 0.5);
-    return __double2float_rn(t);
-}
-
 __global__ void __launch_bounds__(128, 12)
 gh_preprocess_kernel(int P,
                      const float* __restrict__ means3D,
@@ -41,7 +33,7 @@ gh_preprocess_kernel(int P,
     // radius 0 <=> "not rendered" (forward.cu:190-191)
     int out_radius = 0;
     int rect_minx = 0, rect_miny = 0, rect_maxx = 0, rect_maxy = 0;
-    GhGeo g; g.x = 0.f; g.y = 0.f; g.ca = 0.f; g.cb = 0.f; g.cc = 0.f; g.op = 0.f; g.thr = -1e30f; g.pd = 0.f;
+    GhGeo g = gh_geo_not_rendered();
     float zview = 0.f;
 
     float px = 0.f, py = 0.f, pz = 0.f;
@@ -51,18 +43,13 @@ gh_preprocess_kernel(int P,
 
     do {
         if (!valid) break;
-        // near cull only (auxiliary.h:154)
-        zview = GH_ADD(__ldg(vm + 14), GH_FMA(pz, __ldg(vm + 10), GH_FMA(px, __ldg(vm + 2), GH_MUL(py, __ldg(vm + 6)))));
-        if (zview <= 0.2f) {
+        // near cull only (auxiliary.h:154); NDC projection, always recomputed (forward.cu:201-206: the means2D
+        // argument is never read)
+        float projx, projy;
+        if (!gh_pre_project(px, py, pz, vm, pm, zview, projx, projy)) {
             if (prefiltered) atomicOr(&ctrl->err_flags, GH_ERR_PREFILTERED);
             break;
         }
-        // NDC projection, always recomputed (forward.cu:201-206: the means2D argument is never read)
-        const float hx = GH_ADD(__ldg(pm + 12), GH_FMA(pz, __ldg(pm + 8), GH_FMA(px, __ldg(pm + 0), GH_MUL(py, __ldg(pm + 4)))));
-        const float hy = GH_ADD(__ldg(pm + 13), GH_FMA(pz, __ldg(pm + 9), GH_FMA(px, __ldg(pm + 1), GH_MUL(py, __ldg(pm + 5)))));
-        const float hw = GH_ADD(__ldg(pm + 15), GH_FMA(pz, __ldg(pm + 11), GH_FMA(px, __ldg(pm + 3), GH_MUL(py, __ldg(pm + 7)))));
-        const float p_w = GH_RCP(GH_ADD(hw, 0.0000001f));
-        const float projx = GH_MUL(hx, p_w), projy = GH_MUL(hy, p_w);
 
         float covx, covz, det, conx, cony, conz;
         if (conic_precomp == nullptr) {
@@ -122,37 +109,10 @@ gh_preprocess_kernel(int P,
             conx = conic_precomp[3 * idx + 0];
             cony = conic_precomp[3 * idx + 1];
             conz = conic_precomp[3 * idx + 2];
-            const float det_inv = GH_FMA(conx, conz, -GH_MUL(cony, cony));
-            if (det_inv == 0.0f) break;
-            det = GH_RCP(det_inv);
-            covx = GH_MUL(conz, det);
-            covz = GH_MUL(conx, det);
+            if (!gh_pre_from_conic(conx, cony, conz, covx, covz, det)) break;
         }
-        // splat extent from the larger eigenvalue (forward.cu:254-257)
-        const float mid = GH_MUL(GH_ADD(covx, covz), 0.5f);
-        const float sq = GH_SQRT(fmaxf(GH_FMA(mid, mid, -det), 0.1f));
-        const float lam = fmaxf(GH_ADD(mid, sq), GH_SUB(mid, sq));
-        const float my_radius = ceilf(GH_MUL(GH_SQRT(lam), 3.0f));
-        const float pix_x = gh_ndc2pix(projx, W), pix_y = gh_ndc2pix(projy, H);
-        const int ri = __float2int_rz(my_radius);
-        // NaN covariance -> NaN radius -> 0: the reference counts such a Gaussian in tiles_touched but never
-        // emits its key (duplicateWithKeys tests radii > 0), leaving an uninitialised record in the list;
-        // dropping it here keeps the histogram and the emit consistent
-        if (ri <= 0) break;
-        int minx, miny, maxx, maxy;
-        gh_get_rect(pix_x, pix_y, ri, gx, gy, minx, miny, maxx, maxy);
-        if ((maxx - minx) * (maxy - miny) == 0) break;
-
-        const float op = opacities[idx];
-        out_radius = ri;
-        g.x = pix_x; g.y = pix_y; g.ca = conx; g.cb = cony; g.cc = conz; g.op = op;
-        g.thr = __logf(255.0f * op) ;          // only used by the conservative cull (slack covers the approx)
-        g.thr = (255.0f * op > 0.f) ? g.thr : -1e30f;
-        const bool pd = (conx > 0.f) && (conz > 0.f) && (conx * conz - cony * cony > 0.f) && (op == op);
-        g.pd = pd ? 1.0f : 0.0f;
-        if (!(op == op)) g.thr = 1e30f;        // NaN opacity blends with alpha 0.99 in the reference (min.f32)
-
-        rect_minx = minx; rect_miny = miny; rect_maxx = maxx; rect_maxy = maxy;
+        out_radius = gh_pre_finish(covx, covz, det, conx, cony, conz, projx, projy, opacities[idx], W, H, gx, gy,
+                                   rect_minx, rect_miny, rect_maxx, rect_maxy, g);
     } while (false);
 
     if (valid) {
@@ -163,20 +123,7 @@ gh_preprocess_kernel(int P,
         gp[1] = make_float4(g.cc, g.op, g.thr, g.pd);
     }
 
-    // per-tile histogram (replaces the reference's per-Gaussian tiles_touched + prefix sum): the warp walks the
-    // flattened list of its (Gaussian, tile) instances (gh_warp_rects).  Neighbouring Gaussians of a strand hit the
-    // same tiles: lanes asking for the same tile in the same round are grouped with match.any and counted with one
-    // atomic.
-    {
-        const int lane = threadIdx.x & 31;
-        const GhWarpRects wr = gh_warp_rects(rect_minx, rect_miny, rect_maxx, rect_maxy, lane);
-        for (int j0 = 0; j0 < wr.total; j0 += 32) {
-            int owner;
-            const int tile = gh_warp_rect_item(wr, j0 + lane, gx, owner);
-            const uint32_t peers = __match_any_sync(0xffffffffu, tile);
-            if (tile >= 0 && lane == __ffs(peers) - 1) atomicAdd(&tile_count[tile], (uint32_t)__popc(peers));
-        }
-    }
+    gh_warp_tile_histogram(rect_minx, rect_miny, rect_maxx, rect_maxy, gx, tile_count);
 }
 
 // markVisible (rasterizer_impl.cu:54-66): near-plane test only.

@@ -64,30 +64,57 @@ __device__ __forceinline__ void gh_rest_store(const float* s_rest, float* __rest
 }
 
 // ------------------------------------------------------------------------------------------------ forward
+// BIN: also run stage 1 of the rasterizer for the Gaussian just projected (what gh_preprocess_kernel does when it is
+// handed the conic): splat radius, tile rectangle, the 32-byte state record of the blend kernels, depth, and the
+// per-tile instance histogram -- the conic, mean and opacity are still in registers, so the rasterizer's own
+// preprocess launch (and its re-read of 28 bytes per Gaussian) disappears from a fused render.  Same device functions
+// as gh_preprocess_kernel (gh_common.cuh), hence bit-identical radii / records / keys.
+template <bool BIN>
 __global__ void __launch_bounds__(GH_PJ_THREADS)
 gh_project_forward_kernel(GhProjArgs A, float* __restrict__ means2D, float* __restrict__ colors,
                           float* __restrict__ opac_out, float* __restrict__ conic_out, float* __restrict__ cov3D_out,
-                          unsigned char* __restrict__ mask_out)
+                          unsigned char* __restrict__ mask_out,
+                          int* __restrict__ radii, GhGeo* __restrict__ geo, float* __restrict__ depth,
+                          uint32_t* __restrict__ tile_count, int gx, int gy)
 {
     __shared__ __align__(16) float s_rest[GH_PJ_THREADS * GH_PJ_REST];
     const int row0 = blockIdx.x * GH_PJ_THREADS;
     const int i = row0 + threadIdx.x;
     if (A.sh_degree > 0) gh_rest_load(s_rest, A.f_rest, A.P, row0);
     __syncthreads();
-    if (i >= A.P) return;
-    GhProjOut o;
-    gh_project_forward_one(A, i, s_rest + threadIdx.x * GH_PJ_REST, cov3D_out != nullptr, o);
-    means2D[3 * (size_t)i] = o.m2[0]; means2D[3 * (size_t)i + 1] = o.m2[1]; means2D[3 * (size_t)i + 2] = o.m2[2];
-    conic_out[3 * (size_t)i] = o.conic[0]; conic_out[3 * (size_t)i + 1] = o.conic[1]; conic_out[3 * (size_t)i + 2] = o.conic[2];
-    mask_out[i] = o.visible ? 1 : 0;
-    opac_out[i] = o.opacity;
-    if (cov3D_out) {
+    int rect_minx = 0, rect_miny = 0, rect_maxx = 0, rect_maxy = 0;
+    if (i < A.P) {
+        GhProjOut o;
+        gh_project_forward_one(A, i, s_rest + threadIdx.x * GH_PJ_REST, cov3D_out != nullptr, o);
+        means2D[3 * (size_t)i] = o.m2[0]; means2D[3 * (size_t)i + 1] = o.m2[1]; means2D[3 * (size_t)i + 2] = o.m2[2];
+        conic_out[3 * (size_t)i] = o.conic[0]; conic_out[3 * (size_t)i + 1] = o.conic[1]; conic_out[3 * (size_t)i + 2] = o.conic[2];
+        mask_out[i] = o.visible ? 1 : 0;
+        opac_out[i] = o.opacity;
+        if (cov3D_out) {
 #pragma unroll
-        for (int k = 0; k < 6; k++) cov3D_out[6 * (size_t)i + k] = o.cov3D[k];
+            for (int k = 0; k < 6; k++) cov3D_out[6 * (size_t)i + k] = o.cov3D[k];
+        }
+        float2* crow = reinterpret_cast<float2*>(colors + (size_t)i * GH_NUM_CHANNELS);
+#pragma unroll
+        for (int k = 0; k < GH_NUM_CHANNELS / 2; k++) crow[k] = make_float2(o.color[2 * k], o.color[2 * k + 1]);
+        if (BIN) {
+            int out_radius = 0;
+            GhGeo g = gh_geo_not_rendered();
+            float zview = 0.f, projx, projy, covx, covz, det;
+            const float px = A.xyz[3 * (size_t)i], py = A.xyz[3 * (size_t)i + 1], pz = A.xyz[3 * (size_t)i + 2];
+            // (culled Gaussians carry conic = 0 -> singular -> radius 0, exactly as in the two-kernel path)
+            if (gh_pre_project(px, py, pz, A.V, A.Pm, zview, projx, projy) &&
+                gh_pre_from_conic(o.conic[0], o.conic[1], o.conic[2], covx, covz, det))
+                out_radius = gh_pre_finish(covx, covz, det, o.conic[0], o.conic[1], o.conic[2], projx, projy, o.opacity,
+                                           A.W, A.H, gx, gy, rect_minx, rect_miny, rect_maxx, rect_maxy, g);
+            radii[i] = out_radius;
+            depth[i] = zview;
+            float4* gp = reinterpret_cast<float4*>(geo + i);
+            gp[0] = make_float4(g.x, g.y, g.ca, g.cb);
+            gp[1] = make_float4(g.cc, g.op, g.thr, g.pd);
+        }
     }
-    float2* crow = reinterpret_cast<float2*>(colors + (size_t)i * GH_NUM_CHANNELS);
-#pragma unroll
-    for (int k = 0; k < GH_NUM_CHANNELS / 2; k++) crow[k] = make_float2(o.color[2 * k], o.color[2 * k + 1]);
+    if (BIN) gh_warp_tile_histogram(rect_minx, rect_miny, rect_maxx, rect_maxy, gx, tile_count);
 }
 
 // ------------------------------------------------------------------------------------------------ backward
@@ -295,11 +322,54 @@ extern "C" int gh_project_forward(
     if (rc != GH_OK) return rc;
     if (!means2D || !colors || !opacities || !conic || !visible) return gh_set_error(GH_E_INVALID_ARG, "gh_project_forward: missing output pointer");
     if ((size_t)colors & 7) return gh_set_error(GH_E_INVALID_ARG, "gh_project_forward: colors must be 8-byte aligned");
-    gh_project_forward_kernel<<<(P + GH_PJ_THREADS - 1) / GH_PJ_THREADS, GH_PJ_THREADS, 0, stream>>>(
-        A, means2D, colors, opacities, conic, cov3D, visible);
+    gh_project_forward_kernel<false><<<(P + GH_PJ_THREADS - 1) / GH_PJ_THREADS, GH_PJ_THREADS, 0, stream>>>(
+        A, means2D, colors, opacities, conic, cov3D, visible, nullptr, nullptr, nullptr, nullptr, 0, 0);
     gh_count_launches(1);
     const cudaError_t e = cudaGetLastError();
     return e == cudaSuccess ? GH_OK : gh_set_error(GH_E_CUDA, cudaGetErrorString(e));
+}
+
+// gh_project_forward + the rasterizer's first phase (gh_forward_preprocess) in one pass over the Gaussians: fills
+// radii and the geometry / image workspaces, runs the tile scan and reads back R like gh_forward_preprocess does;
+// continue with gh_forward_render.
+extern "C" int gh_project_forward_binned(
+    int P, int width, int height,
+    const float* xyz, const float* scaling, const float* rotation, const float* dirs,
+    const float* features_dc, const float* features_rest,
+    const float* opacity, const float* label, const float* orient_conf,
+    const float* viewmatrix, const float* projmatrix, const float* campos,
+    float tan_fovx, float tan_fovy, float scale_modifier, int sh_degree, unsigned int flags, float det_eps,
+    float* means2D, float* colors, float* opacities, float* conic, float* cov3D, unsigned char* visible,
+    int* radii, char* geom_buffer, char* img_buffer, int* num_rendered, int* max_tile_len,
+    gh_stream_t stream_)
+{
+    cudaStream_t stream = (cudaStream_t)stream_;
+    gh_clear_error();
+    GhProjArgs A = gh_proj_args(P, width, height, xyz, scaling, rotation, dirs, features_dc, features_rest, opacity, label,
+                                orient_conf, viewmatrix, projmatrix, campos, tan_fovx, tan_fovy, scale_modifier, sh_degree, flags, det_eps);
+    const int rc = gh_proj_check(A, "gh_project_forward_binned");
+    if (rc != GH_OK) return rc;
+    if (!means2D || !colors || !opacities || !conic || !visible || !radii || !geom_buffer || !img_buffer || !num_rendered)
+        return gh_set_error(GH_E_INVALID_ARG, "gh_project_forward_binned: missing output pointer");
+    if ((size_t)colors & 7) return gh_set_error(GH_E_INVALID_ARG, "gh_project_forward_binned: colors must be 8-byte aligned");
+    const int gx = (width + GH_BLOCK_X - 1) / GH_BLOCK_X, gy = (height + GH_BLOCK_Y - 1) / GH_BLOCK_Y;
+    const int T = gx * gy;
+    GhGeomWS geom = GhGeomWS::carve(geom_buffer, (size_t)P);
+    GhImgWS img = GhImgWS::carve(img_buffer, (size_t)width * height, (size_t)T);
+    // ctrl + tile histogram are contiguous: one memset
+    cudaError_t e = cudaMemsetAsync(img.ctrl, 0, 256 + gh_align_up((size_t)T * 4, 256), stream);
+    if (e != cudaSuccess) return gh_set_error(GH_E_CUDA, "gh_project_forward_binned: memset(tile histogram) failed");
+    gh_project_forward_kernel<true><<<(P + GH_PJ_THREADS - 1) / GH_PJ_THREADS, GH_PJ_THREADS, 0, stream>>>(
+        A, means2D, colors, opacities, conic, cov3D, visible, radii, geom.geo, geom.depth, img.tile_count, gx, gy);
+    gh_launch_tile_scan(T, img, stream);
+    gh_count_launches(2);
+    GhCtrl h;
+    e = cudaMemcpyAsync(&h, img.ctrl, sizeof(GhCtrl), cudaMemcpyDeviceToHost, stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(stream);
+    if (e != cudaSuccess) return gh_set_error(GH_E_CUDA, cudaGetErrorString(e));
+    *num_rendered = (int)h.num_rendered;
+    if (max_tile_len) *max_tile_len = (int)h.max_tile_len;
+    return GH_OK;
 }
 
 extern "C" int gh_project_backward(

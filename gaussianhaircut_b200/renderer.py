@@ -83,6 +83,15 @@ class _FusedRender(torch.autograd.Function):
         P = n_head + P_own
         pi = projection.pack_inputs(xyz, scaling, rotation, dirs, f_dc, f_rest, opacity, label, conf, viewmatrix, projmatrix,
                                     campos, st["tanx"], st["tany"], st["W"], st["H"], st["sh_degree"], st["mod"], st["cfg"])
+        bg = st["bg"]
+        if n_head == 0 and P_own > 0 and not st["debug"]:
+            # one pass over the Gaussians does the projection AND the rasterizer's preprocess + tile histogram
+            out, radii, geom, img, R, max_len = projection.project_forward_binned(pi, means2D_out=viewspace.detach())
+            color, binning = _C.forward_render(bg, out["colors"], radii, geom, img, R, max_len, st["H"], st["W"])
+            ctx.pi, ctx.st, ctx.R, ctx.n_head, ctx.hp = pi, st, R, 0, None
+            ctx.bufs = (pi.xyz, out["colors"], out["conic"], out["visible"], radii, geom, binning, img)
+            ctx.mark_non_differentiable(radii)
+            return color, radii
         if n_head == 0:
             out = projection.project_forward(pi, means2D_out=viewspace.detach())
             means3D = pi.xyz
@@ -96,7 +105,6 @@ class _FusedRender(torch.autograd.Function):
             projection.project_forward(hp, out=sl(0, n_head))
             projection.project_forward(pi, out=sl(n_head, P))
             means3D = torch.cat([hp.xyz, pi.xyz], dim=0)
-        bg = st["bg"]
         R, color, radii, geom, binning, img = _C.rasterize_gaussians(
             bg, means3D, _EMPTY, out["colors"], out["opacity"], _EMPTY, _EMPTY, st["mod"], _EMPTY, out["conic"],
             pi.V, pi.Pm, st["tanx"], st["tany"], st["H"], st["W"], _EMPTY, st["sh_degree"], pi.campos,

@@ -278,6 +278,21 @@ int gh_project_forward(
     float tan_fovx, float tan_fovy, float scale_modifier, int sh_degree, unsigned int flags, float det_eps,
     float* means2D, float* colors, float* opacities, float* conic, float* cov3D, unsigned char* visible,
     gh_stream_t stream);
+/* gh_project_forward + gh_forward_preprocess in ONE pass over the Gaussians (the fused render path): besides the
+ * outputs of gh_project_forward it fills `radii` and the geometry / image workspaces exactly as gh_forward_preprocess
+ * would when handed (xyz, conic, opacities) with prefiltered = 0 -- same device code, bit-identical radii, state
+ * records and keys -- runs the tile scan and returns num_rendered / max_tile_len after the same 16-byte read-back.
+ * Continue with gh_binning_workspace_size + gh_forward_render.  Workspaces: gh_forward_workspace_sizes. */
+int gh_project_forward_binned(
+    int P, int width, int height,
+    const float* xyz, const float* scaling, const float* rotation, const float* dirs,
+    const float* features_dc, const float* features_rest,
+    const float* opacity, const float* label, const float* orient_conf,
+    const float* viewmatrix, const float* projmatrix, const float* campos,
+    float tan_fovx, float tan_fovy, float scale_modifier, int sh_degree, unsigned int flags, float det_eps,
+    float* means2D, float* colors, float* opacities, float* conic, float* cov3D, unsigned char* visible,
+    int* radii, char* geom_buffer, char* img_buffer, int* num_rendered, int* max_tile_len,
+    gh_stream_t stream);
 int gh_project_backward(
     int P, int width, int height,
     const float* xyz, const float* scaling, const float* rotation, const float* dirs,

@@ -100,6 +100,43 @@ def test_projection_kernels_match_autograd(cuda_device, flavour, strands, W, H, 
     assert torch.equal(d2["viewmatrix"], d["viewmatrix"]) and torch.equal(d2["projmatrix"], d["projmatrix"])
 
 
+@pytest.mark.parametrize("flavour,strands,W,H,view", [("gaussian_model", 5000, 1920, 1080, 19), ("hair", 5000, 1920, 1080, 3)])
+def test_binned_projection_is_bit_identical_to_the_two_kernel_path(cuda_device, flavour, strands, W, H, view):
+    """gh_project_forward_binned (projection + the rasterizer's first phase in one pass) against gh_project_forward
+    followed by the rasterizer's own preprocess on its outputs: same radii, R, workspaces' content as seen by the
+    second phase (the rendered image), bit for bit."""
+    from gaussianhaircut_b200 import projection, _C
+    synth = _util.synth
+    dev = cuda_device
+    scene = synth.make_strand_scene(strands, seed=4)
+    cam = synth.make_camera(view, W, H)
+    cfg = dict(synth.PROJECT_GAUSSIAN_MODEL if flavour == "gaussian_model" else synth.PROJECT_HAIR_MODEL)
+    raw = {k: v.to(dev) for k, v in synth.raw_params_from_scene(scene, flavour).items()}
+    if flavour == "gaussian_model":
+        raw["xyz"][::97] += torch.tensor([0.0, 0.0, -5.0], device=dev)          # some Gaussians behind the camera / culled
+    pi = projection.pack_inputs(raw["xyz"], raw["scaling"], raw["rotation"], raw.get("dirs"), raw["f_dc"], raw["f_rest"],
+                                raw.get("opacity"), raw.get("label"), raw.get("conf"), cam["world_view_transform"].to(dev),
+                                cam["full_proj_transform"].to(dev), cam["camera_center"].to(dev), cam["tanfovx"], cam["tanfovy"],
+                                W, H, 3, 1.0, cfg)
+    bg = torch.tensor(synth.BG_DEFAULT, device=dev)
+    empty = torch.empty(0)
+    a = projection.project_forward(pi)
+    Ra, color_a, radii_a, geom_a, bin_a, img_a = _C.rasterize_gaussians(
+        bg, pi.xyz, empty, a["colors"], a["opacity"], empty, empty, 1.0, empty, a["conic"], pi.V, pi.Pm, cam["tanfovx"], cam["tanfovy"],
+        H, W, empty, 3, pi.campos, False, False)
+    b, radii_b, geom_b, img_b, Rb, max_len = projection.project_forward_binned(pi)
+    color_b, bin_b = _C.forward_render(bg, b["colors"], radii_b, geom_b, img_b, Rb, max_len, H, W)
+    torch.cuda.synchronize()
+    assert Ra == Rb and Ra > 0
+    for k in ("means2D", "colors", "opacity", "conic", "visible"):
+        assert torch.equal(a[k], b[k]), k
+    assert torch.equal(radii_a, radii_b)
+    if flavour == "gaussian_model":
+        assert int((radii_a > 0).sum()) < radii_a.numel()                          # view 19 sees the displaced rows behind it: culled rows exist
+    assert torch.equal(color_a, color_b)
+    assert torch.equal(bin_a[:8 * Ra], bin_b[:8 * Rb])                             # sorted (depth | index) records of every tile
+
+
 def _weights(H, W, device, seed):
     g = torch.Generator().manual_seed(seed)
     return {k: torch.rand(c, H, W, generator=g).to(device) for k, c in (("render", 3), ("mask", 2), ("orient_angle", 1), ("orient_conf", 1))}
