@@ -167,6 +167,8 @@ int gh_forward_preprocess(
 
     int gx, gy; gh_grid(width, height, gx, gy);
     const int T = gx * gy;
+    if ((unsigned long long)gx * gx * gy >= (1ull << 32))     // exactness bound of the tile enumeration (gh_warp_rects)
+        return gh_fail(GH_E_INVALID_ARG, "gh_forward_preprocess: image too large (tile grid gx * gx * gy must stay below 2^32)");
     GhGeomWS geom = GhGeomWS::carve(geom_buffer, (size_t)P);
     GhImgWS img = GhImgWS::carve(img_buffer, (size_t)width * height, (size_t)T);
 

@@ -200,7 +200,9 @@ __device__ __forceinline__ GhGeo gh_geo_not_rendered() {
 // list (warp prefix sum of their sizes) and lane l takes items l, l + 32, ...: ceil(sum / 32) rounds instead of max.
 struct GhWarpRects {
     int incl, excl, w, minxy, total;
-    uint32_t rw;       // ceil(2^32 / w): k / w == umulhi(k, rw) for k * w < 2^32 (w >= 2)
+    uint32_t rw;       // ceil(2^32 / w): k / w == umulhi(k, rw) whenever k * w < 2^32 (w >= 2).  k < w * h for a
+                       // rectangle of w x h tiles, so every tile grid with gx * gx * gy < 2^32 is safe (checked by the
+                       // host entry points; 1080p: 120 * 120 * 68 = 979 200)
 };
 __device__ __forceinline__ GhWarpRects gh_warp_rects(int minx, int miny, int maxx, int maxy, int lane) {
     GhWarpRects r;

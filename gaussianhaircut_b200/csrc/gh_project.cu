@@ -354,6 +354,8 @@ extern "C" int gh_project_forward_binned(
     if ((size_t)colors & 7) return gh_set_error(GH_E_INVALID_ARG, "gh_project_forward_binned: colors must be 8-byte aligned");
     const int gx = (width + GH_BLOCK_X - 1) / GH_BLOCK_X, gy = (height + GH_BLOCK_Y - 1) / GH_BLOCK_Y;
     const int T = gx * gy;
+    if ((unsigned long long)gx * gx * gy >= (1ull << 32))     // exactness bound of the tile enumeration (gh_warp_rects)
+        return gh_set_error(GH_E_INVALID_ARG, "gh_project_forward_binned: image too large (tile grid gx * gx * gy must stay below 2^32)");
     GhGeomWS geom = GhGeomWS::carve(geom_buffer, (size_t)P);
     GhImgWS img = GhImgWS::carve(img_buffer, (size_t)width * height, (size_t)T);
     // ctrl + tile histogram are contiguous: one memset

@@ -80,8 +80,26 @@ def test_argument_validation_without_gpu(lib):
     with pytest.raises(_capi.GhError) as ei:
         _capi.check(rc)
     assert ei.value.code == _capi.GH_E_INVALID_ARG
+    # an image whose tile grid leaves the exactness range of the tile enumeration (gx * gx * gy < 2^32) is refused
+    rc = lib.gh_forward_preprocess(10, 3, 0, 40000, 40000, fake, None, None, fake, fake, fake, 1.0, C.c_void_p(0x1000), None,
+                                   None, fake, fake, fake, 0.5, 0.5, 0, fake, fake, fake, C.byref(n), C.byref(m), 0, None)
+    assert rc == _capi.GH_E_INVALID_ARG and b"image too large" in lib.gh_last_error()
     assert lib.gh_mark_visible(0, None, None, None, None, None) == 0
     assert lib.gh_kernel_launch_count() == 0      # nothing was launched by any of the above
+
+
+def test_tile_enumeration_division_is_exact_in_the_accepted_range():
+    """gh_warp_rect_item (csrc/gh_common.cuh) turns item k of a w-tile-wide rectangle into (row, column) with
+    q = umulhi(k, ceil(2^32 / w)).  That equals k // w whenever k * w < 2^32; k < w * h <= gx * gy, and the entry points
+    refuse grids with gx * gx * gy >= 2^32.  Checked here on the arithmetic itself (numpy, same integer formula)."""
+    import numpy as np
+    rng = np.random.default_rng(0)
+    for w in list(range(2, 300)) + [511, 512, 513, 1023, 1039, 1600, 2047, 2048, 4095]:
+        rw = np.uint64((0xFFFFFFFF // w + 1) & 0xFFFFFFFF)
+        kmax = min((1 << 32) // w, 1 << 26)                      # k * w < 2^32
+        k = np.unique(np.concatenate([np.arange(0, min(kmax, 1 << 16)), rng.integers(0, kmax, 1 << 16), [kmax - 1]])).astype(np.uint64)
+        q = (k * rw) >> np.uint64(32)
+        assert np.array_equal(q, k // np.uint64(w)), w
 
 
 def test_missing_library_fails_loudly(tmp_path):
