@@ -141,7 +141,9 @@ def densify_and_prune(gaussians, max_grad: float, min_opacity: float, extent: fl
         if p.shape[0] != P or p.dtype != torch.float32 or not p.is_contiguous():
             raise RuntimeError(f"densify: parameter group '{n}' must be a contiguous float32 tensor with {P} rows")
         st = opt.state.get(p, None)
-        row = p.numel() // max(P, 1) if P > 0 else int(torch.tensor(p.shape[1:]).prod()) if p.dim() > 1 else 1
+        row = 1
+        for d in p.shape[1:]:
+            row *= int(d)
         new_p = _pool_alloc(gaussians, n, P_new, p.shape[1:], dev, p)
         srcs.append(p.detach()); rows.append(row); dsts.append(new_p)
         if st is not None and "exp_avg" in st:
